@@ -1,0 +1,654 @@
+// abo_api.cu — C ABI of libabo_cuda.so (include/abo.h): handles, host drivers of the blocked
+// Cholesky / triangular inverse / candidate sweep, top-k selection.  No CPU fallback anywhere:
+// every entry point needs a live CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/abo.h"
+#include "gemm_dmma.cuh"
+#include "kernels.cuh"
+#include "abo_internal.h"
+
+using namespace abo;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+int abo_fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+extern "C" const char* abo_last_error(void) { return g_err.c_str(); }
+extern "C" int32_t abo_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+static int configure_kernels() {
+    CU(configure_gemm<KC, KC, EPI_STORE>());
+    CU(configure_gemm<KC, MC, EPI_STORE>());
+    CU(configure_gemm<MC, MC, EPI_STORE>());
+    CU(configure_gemm<KC, KC, EPI_SUMSQ>());
+    CU(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM_BYTES));
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_ctx_create(int32_t device, abo_ctx** out) {
+    if (!out) return abo_fail(ABO_ERR_INVALID, "abo_ctx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return abo_fail(ABO_ERR_CUDA, "no CUDA device available (%s); libabo_cuda has no CPU fallback",
+                        e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return abo_fail(ABO_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return abo_fail(ABO_ERR_CUDA, "device %d is sm_%d%d; libabo_cuda is built for sm_100a only", device, prop.major,
+                        prop.minor);
+    abo_ctx* c = new (std::nothrow) abo_ctx();
+    if (!c) return abo_fail(ABO_ERR_ALLOC, "host allocation failed");
+    c->device = device;
+    c->sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+    int rc = configure_kernels();
+    if (rc) return rc;
+    *out = c;
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_ctx_destroy(abo_ctx* c) {
+    if (!c) return ABO_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& b : c->ws) if (b.ptr) cudaFree(b.ptr);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    abo_nccl_teardown(c);
+    cudaEventDestroy(c->ev_a);
+    cudaEventDestroy(c->ev_b);
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->stream2);
+    delete c;
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_ctx_device(const abo_ctx* c, int32_t* device) {
+    if (!c || !device) return abo_fail(ABO_ERR_INVALID, "null argument");
+    *device = c->device;
+    return ABO_OK;
+}
+extern "C" int32_t abo_ctx_stream(const abo_ctx* c, void** stream) {
+    if (!c || !stream) return abo_fail(ABO_ERR_INVALID, "null argument");
+    *stream = (void*)c->stream;
+    return ABO_OK;
+}
+extern "C" int32_t abo_ctx_launch_count(const abo_ctx* c, int64_t* count) {
+    if (!c || !count) return abo_fail(ABO_ERR_INVALID, "null argument");
+    *count = c->launches;
+    return ABO_OK;
+}
+
+// grow-only workspace slots
+int ws_get(abo_ctx* c, int slot, size_t bytes, void** out) {
+    auto& b = c->ws[slot];
+    if (b.bytes < bytes) {
+        if (b.ptr) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(b.ptr)); b.ptr = nullptr; b.bytes = 0; }
+        cudaError_t e = cudaMalloc(&b.ptr, bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); return abo_fail(ABO_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+        b.bytes = bytes;
+    }
+    *out = b.ptr;
+    return ABO_OK;
+}
+
+int pinned_get(abo_ctx* c, size_t bytes, void** out) {
+    if (c->pinned_bytes < bytes) {
+        if (c->pinned) { CU(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->pinned); c->pinned = nullptr; c->pinned_bytes = 0; }
+        cudaError_t e = cudaMallocHost(&c->pinned, bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); return abo_fail(ABO_ERR_ALLOC, "cudaMallocHost(%zu) failed", bytes); }
+        c->pinned_bytes = bytes;
+    }
+    *out = c->pinned;
+    return ABO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// blocked Cholesky (right-looking, NB = 128): potf2+inverse of the diagonal block (1 CTA),
+// panel TRSM as a DMMA GEMM with the block inverse, SYRK trailing update as a DMMA GEMM.
+// A: batch matrices, row-major, Npad x Npad (ld), lower triangle referenced.
+// Dinv: batch x T x 128 x 128 block inverses.  info: batch ints (0 = ok).
+// ------------------------------------------------------------------------------------------
+int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strideA, double* Dinv, int64_t strideD,
+                  int* info, int batch) {
+    const int T = (int)(Npad / NB);
+    cudaStream_t st = c->stream;
+    for (int jb = 0; jb < T; ++jb) {
+        double* Ajj = A + (int64_t)jb * NB * (ld + 1);
+        double* Dj = Dinv + (int64_t)jb * NB * NB;
+        potf2_inv_kernel<<<batch, 512, POTF2_SMEM_BYTES, st>>>(Ajj, ld, strideA, Dj, strideD, info, jb * NB);
+        KL(c);
+        const int rem = (int)(Npad - (int64_t)(jb + 1) * NB);
+        if (rem <= 0) break;
+        double* P = Ajj + (int64_t)NB * ld;            // panel below the diagonal block
+        GemmParams g{};
+        g.A = P; g.lda = ld; g.strideA = strideA;
+        g.B = Dj; g.ldb = NB; g.strideB = strideD;
+        g.C = P; g.ldc = ld; g.strideC = strideA;
+        g.M = rem; g.N = NB; g.K = NB; g.alpha = 1.0; g.beta = 0.0; g.flags = 0;
+        CU((launch_gemm<KC, KC, EPI_STORE>(g, batch, st)));   // L_ij = A_ij * inv(L_jj)^T
+        KL(c);
+        GemmParams s{};
+        s.A = P; s.lda = ld; s.strideA = strideA;
+        s.B = P; s.ldb = ld; s.strideB = strideA;
+        s.C = Ajj + (int64_t)NB * (ld + 1); s.ldc = ld; s.strideC = strideA;
+        s.M = rem; s.N = rem; s.K = NB; s.alpha = -1.0; s.beta = 1.0; s.flags = LOWER_ONLY;
+        CU((launch_gemm<KC, KC, EPI_STORE>(s, batch, st)));   // A_22 -= L_21 L_21^T
+        KL(c);
+    }
+    return ABO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// triangular inverse  Linv = L^-1  by recursive doubling on tiles: the diagonal tiles are the
+// block inverses from potf2; at level b (tiles) every pair computes
+//     X21 = - X22 * (L21 * X11)
+// as two batched DMMA GEMMs that skip the structurally-zero k-ranges.  W: scratch, same shape.
+// ------------------------------------------------------------------------------------------
+int trtri_blocked(abo_ctx* c, const double* L, double* Linv, double* W, int64_t Npad, int64_t ld, int64_t strideM,
+                  const double* Dinv, int64_t strideD, int batch) {
+    const int T = (int)(Npad / NB);
+    cudaStream_t st = c->stream;
+    place_diag_kernel<<<dim3(T, batch), 256, 0, st>>>(Dinv, Linv, ld, strideD, strideM);
+    KL(c);
+    for (int b = 1; b < T; b <<= 1) {
+        // pairs start at tile o = 2*b*q; rows22 = [o+b, min(o+2b, T)).  For a single matrix all full
+        // pairs of a level go out as one launch batched over q; a ragged last pair goes separately.
+        const int npairs = (T - b + 2 * b - 1) / (2 * b);          // pairs with a non-empty block 22
+        const int nfull = T / (2 * b);                             // pairs with a full block 22
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int grp = 0; grp < 2; ++grp) {
+                int q0, nq, r22;
+                if (batch == 1) {
+                    if (grp == 0) { q0 = 0; nq = nfull; r22 = b; }
+                    else { q0 = nfull; nq = npairs - nfull; r22 = (nq > 0) ? (T - 2 * b * nfull - b) : 0; }
+                    if (nq <= 0 || r22 <= 0) continue;
+                } else {
+                    if (grp == 1) continue;
+                    q0 = 0; nq = npairs; r22 = b;                  // handled pair by pair below
+                }
+                for (int q = q0; q < q0 + (batch == 1 ? 1 : nq); ++q) {
+                    const int o = 2 * b * q;
+                    const int rr = (batch == 1) ? r22 : (std::min(2 * b, T - o) - b);
+                    const int zb = (batch == 1) ? nq : batch;
+                    const int64_t zs = (batch == 1) ? (int64_t)2 * b * NB * (ld + 1) : strideM;
+                    const int64_t off11 = (int64_t)o * NB * (ld + 1);
+                    const int64_t off22 = (int64_t)(o + b) * NB * (ld + 1);
+                    const int64_t off21 = (int64_t)(o + b) * NB * ld + (int64_t)o * NB;
+                    GemmParams g{};
+                    if (pass == 0) {                              // W21 = L21 * X11   (X11 lower: k >= n)
+                        g.A = L + off21; g.B = Linv + off11; g.C = W + off21;
+                        g.M = rr * NB; g.N = b * NB; g.K = b * NB; g.alpha = 1.0; g.flags = KLO_N;
+                    } else {                                      // X21 = -X22 * W21  (X22 lower: k <= m)
+                        g.A = Linv + off22; g.B = W + off21; g.C = Linv + off21;
+                        g.M = rr * NB; g.N = b * NB; g.K = rr * NB; g.alpha = -1.0; g.flags = KHI_M;
+                    }
+                    g.lda = g.ldb = g.ldc = ld; g.strideA = g.strideB = g.strideC = zs; g.beta = 0.0;
+                    CU((launch_gemm<KC, MC, EPI_STORE>(g, zb, st)));
+                    KL(c);
+                }
+            }
+        }
+    }
+    return ABO_OK;
+}
+
+// beta = Linv * delta ; alpha = Linv^T * beta      (alpha = (K + noise I)^-1 (y - m))
+int solve_alpha(abo_ctx* c, const double* Linv, int64_t ld, int64_t N, const double* delta, double* beta,
+                double* alpha, int64_t strideM, int64_t strideV, int batch) {
+    cudaStream_t st = c->stream;
+    {
+        int64_t threads = N * 32;
+        dim3 grid((unsigned)((threads + 255) / 256), batch);
+        trmv_lower_kernel<<<grid, 256, 0, st>>>(Linv, ld, N, delta, beta, strideM, strideV);
+        KL(c);
+    }
+    const int nchunks = (int)((N + TRMVT_ROWS - 1) / TRMVT_ROWS);
+    double* part;
+    int rc = ws_get(c, WS_VEC_PART, sizeof(double) * (size_t)nchunks * N * batch, (void**)&part);
+    if (rc) return rc;
+    {
+        dim3 grid((unsigned)((N + 127) / 128), nchunks, batch);
+        trmvT_lower_partial_kernel<<<grid, 128, 0, st>>>(Linv, ld, N, beta, part, strideM, strideV, (int64_t)nchunks * N);
+        KL(c);
+        dim3 g2((unsigned)((N + 127) / 128), batch);
+        reduce_rows_kernel<<<g2, 128, 0, st>>>(part, nchunks, N, alpha, (int64_t)nchunks * N, strideV);
+        KL(c);
+    }
+    return ABO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// surrogate handle
+// ------------------------------------------------------------------------------------------
+static void gp_free_device(abo_gp* g) {
+    cudaSetDevice(g->ctx->device);
+    double** ptrs[] = {&g->dXsT, &g->dL, &g->dLinv, &g->dAlpha, &g->dBeta, &g->dDelta, &g->dMeanC};
+    for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+    g->fitted = false;
+    g->cap_pad = 0;
+}
+
+static int gp_alloc(abo_gp* g, int64_t Npad, int64_t ldx) {
+    gp_free_device(g);
+    size_t mat = sizeof(double) * (size_t)Npad * Npad;
+    cudaError_t e;
+    if ((e = cudaMalloc(&g->dL, mat)) != cudaSuccess || (e = cudaMalloc(&g->dLinv, mat)) != cudaSuccess ||
+        (e = cudaMalloc(&g->dXsT, sizeof(double) * (size_t)ldx * g->d)) != cudaSuccess ||
+        (e = cudaMalloc(&g->dAlpha, sizeof(double) * Npad)) != cudaSuccess ||
+        (e = cudaMalloc(&g->dBeta, sizeof(double) * Npad)) != cudaSuccess ||
+        (e = cudaMalloc(&g->dDelta, sizeof(double) * Npad)) != cudaSuccess ||
+        (e = cudaMalloc(&g->dMeanC, sizeof(double) * g->p)) != cudaSuccess) {
+        cudaGetLastError();
+        gp_free_device(g);
+        return abo_fail(ABO_ERR_ALLOC, "device allocation for a %lld x %lld posterior failed: %s", (long long)Npad,
+                        (long long)Npad, cudaGetErrorString(e));
+    }
+    g->cap_pad = Npad;
+    g->ld = Npad;
+    g->ldx = ldx;
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_gp_create(abo_ctx* ctx, int32_t kernel_id, int32_t d, int32_t p, abo_gp** out) {
+    if (!ctx || !out) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (kernel_id < 0 || kernel_id > 6) return abo_fail(ABO_ERR_INVALID, "unknown kernel id %d", kernel_id);
+    if (d < 1) return abo_fail(ABO_ERR_INVALID, "d must be >= 1");
+    if (p != 1 && p != d + 1) return abo_fail(ABO_ERR_INVALID, "p must be 1 (StandardGP) or d+1 (GradientGP)");
+    if (p > 1 && (kernel_id == ABO_KERNEL_MATERN52 || kernel_id == ABO_KERNEL_MATERN72))
+        return abo_fail(ABO_ERR_INVALID,
+                        "KernelFunctions Matern kernels are not differentiable at 0 (NaN, test/test_kernels.jl:87); "
+                        "use the Approx/AD variants for GradientGP");
+    abo_gp* g = new (std::nothrow) abo_gp();
+    if (!g) return abo_fail(ABO_ERR_ALLOC, "host allocation failed");
+    g->ctx = ctx; g->kind = kernel_id; g->d = d; g->p = p;
+    g->s = 1.0; g->scale = 1.0; g->noise = 0.0;
+    g->mean_c.assign(p, 0.0);
+    *out = g;
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_gp_destroy(abo_gp* g) {
+    if (!g) return ABO_OK;
+    gp_free_device(g);
+    delete g;
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_gp_set_params(abo_gp* g, double inv_ls, double scale, double noise, const double* mean_c) {
+    if (!g) return abo_fail(ABO_ERR_INVALID, "null gp");
+    if (!(inv_ls > 0) || !(scale > 0) || !(noise >= 0) || !std::isfinite(inv_ls) || !std::isfinite(scale))
+        return abo_fail(ABO_ERR_INVALID, "hyper-parameters must be positive and finite (noise >= 0)");
+    g->s = inv_ls; g->scale = scale; g->noise = noise;
+    for (int a = 0; a < g->p; ++a) g->mean_c[a] = mean_c ? mean_c[a] : 0.0;
+    g->fitted = false;
+    return ABO_OK;
+}
+
+static KSpec gp_spec(const abo_gp* g) {
+    KSpec k;
+    k.kind = g->kind; k.d = g->d; k.p = g->p; k.s = g->s; k.scale = g->scale; k.noise = g->noise;
+    return k;
+}
+
+extern "C" int32_t abo_gp_fit(abo_gp* g, const double* X, const double* y, int64_t n, int64_t* info_out) {
+    if (!g || !X || !y) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (n < 1) return abo_fail(ABO_ERR_DIM, "need at least one observation");
+    abo_ctx* c = g->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int64_t N = n * g->p;
+    const int64_t Npad = (N + NB - 1) / NB * NB;
+    const int64_t ldx = (n + NB - 1) / NB * NB + NB;      // room for appended points
+    g->fitted = false;
+    if (Npad != g->cap_pad || ldx > g->ldx) { int rc = gp_alloc(g, Npad, ldx); if (rc) return rc; }
+    g->n = n; g->N = N; g->Npad = Npad;
+    g->hX.assign(X, X + n * g->d);
+    g->hY.assign(y, y + N);
+
+    // stage X, y
+    double *dXraw, *dYraw;
+    int rc;
+    if ((rc = ws_get(c, WS_STAGE_X, sizeof(double) * (size_t)n * g->d, (void**)&dXraw))) return rc;
+    if ((rc = ws_get(c, WS_STAGE_Y, sizeof(double) * (size_t)N, (void**)&dYraw))) return rc;
+    CU(cudaMemcpyAsync(dXraw, X, sizeof(double) * n * g->d, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dYraw, y, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(g->dMeanC, g->mean_c.data(), sizeof(double) * g->p, cudaMemcpyHostToDevice, st));
+    {
+        int64_t tot = g->ldx * g->d;
+        scale_transpose_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(dXraw, g->dXsT, n, g->d, g->ldx, g->s);
+        KL(c);
+        fill_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(g->dDelta, Npad, 0.0);
+        KL(c);
+        delta_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(dYraw, g->dMeanC, n, g->p, g->dDelta);
+        KL(c);
+    }
+    const int T = (int)(Npad / NB);
+    KmatBatch bt{nullptr, nullptr, 0, 0};
+    kmat_kernel<<<dim3(T, T, 1), 256, 0, st>>>(gp_spec(g), g->dXsT, g->ldx, N, g->dL, g->ld, bt);
+    KL(c);
+
+    double* Dinv; int* dinfo; double* W;
+    if ((rc = ws_get(c, WS_DINV, sizeof(double) * (size_t)T * NB * NB, (void**)&Dinv))) return rc;
+    if ((rc = ws_get(c, WS_INFO, sizeof(int) * 16, (void**)&dinfo))) return rc;
+    if ((rc = ws_get(c, WS_TRTRI, sizeof(double) * (size_t)Npad * Npad, (void**)&W))) return rc;
+    CU(cudaMemsetAsync(dinfo, 0, sizeof(int) * 16, st));
+    if ((rc = potrf_blocked(c, g->dL, Npad, g->ld, 0, Dinv, 0, dinfo, 1))) return rc;
+    int hinfo = 0;
+    CU(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (info_out) *info_out = hinfo;
+    if (hinfo != 0)
+        return abo_fail(ABO_ERR_NOT_POSDEF, "matrix is not positive definite; Cholesky factorization failed at pivot %d", hinfo);
+    if ((rc = trtri_blocked(c, g->dL, g->dLinv, W, Npad, g->ld, 0, Dinv, 0, 1))) return rc;
+    if ((rc = solve_alpha(c, g->dLinv, g->ld, Npad, g->dDelta, g->dBeta, g->dAlpha, 0, 0, 1))) return rc;
+    CU(cudaStreamSynchronize(st));
+    g->fitted = true;
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_gp_clone(const abo_gp* g, abo_gp** out) {
+    if (!g || !out) return abo_fail(ABO_ERR_INVALID, "null argument");
+    abo_gp* n = new (std::nothrow) abo_gp(*g);
+    if (!n) return abo_fail(ABO_ERR_ALLOC, "host allocation failed");
+    n->dXsT = n->dL = n->dLinv = n->dAlpha = n->dBeta = n->dDelta = n->dMeanC = nullptr;
+    n->cap_pad = 0; n->fitted = false;
+    if (g->cap_pad > 0) {
+        abo_ctx* c = g->ctx;
+        CU(cudaSetDevice(c->device));
+        int rc = gp_alloc(n, g->cap_pad, g->ldx);
+        if (rc) { delete n; return rc; }
+        cudaStream_t st = c->stream;
+        size_t mat = sizeof(double) * (size_t)g->cap_pad * g->cap_pad;
+        CU(cudaMemcpyAsync(n->dL, g->dL, mat, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(n->dLinv, g->dLinv, mat, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(n->dXsT, g->dXsT, sizeof(double) * g->ldx * g->d, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(n->dAlpha, g->dAlpha, sizeof(double) * g->cap_pad, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(n->dBeta, g->dBeta, sizeof(double) * g->cap_pad, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(n->dDelta, g->dDelta, sizeof(double) * g->cap_pad, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(n->dMeanC, g->dMeanC, sizeof(double) * g->p, cudaMemcpyDeviceToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        n->fitted = g->fitted;
+    }
+    *out = n;
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_gp_n(const abo_gp* g, int64_t* n) {
+    if (!g || !n) return abo_fail(ABO_ERR_INVALID, "null argument");
+    *n = g->fitted ? g->n : 0;
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_gp_alpha(const abo_gp* g, double* alpha) {
+    if (!g || !alpha) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (!g->fitted) return abo_fail(ABO_ERR_NOT_FITTED, "surrogate has no posterior");
+    abo_ctx* c = g->ctx;
+    CU(cudaSetDevice(c->device));
+    double* tmp;
+    int rc = ws_get(c, WS_STAGE_Y, sizeof(double) * (size_t)g->N, (void**)&tmp);
+    if (rc) return rc;
+    to_out_major_kernel<<<(unsigned)((g->N + 255) / 256), 256, 0, c->stream>>>(g->dAlpha, g->n, g->p, tmp);
+    KL(c);
+    CU(cudaMemcpyAsync(alpha, tmp, sizeof(double) * g->N, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_gp_factor(const abo_gp* g, int32_t which, double* out) {
+    if (!g || !out) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (!g->fitted) return abo_fail(ABO_ERR_NOT_FITTED, "surrogate has no posterior");
+    CU(cudaSetDevice(g->ctx->device));
+    const double* src = which == 0 ? g->dL : g->dLinv;
+    CU(cudaMemcpy2DAsync(out, sizeof(double) * g->N, src, sizeof(double) * g->ld, sizeof(double) * g->N, g->N,
+                         cudaMemcpyDeviceToHost, g->ctx->stream));
+    CU(cudaStreamSynchronize(g->ctx->stream));
+    return ABO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// candidate sweep
+// ------------------------------------------------------------------------------------------
+template <int DT>
+static void launch_ks(abo_ctx* c, const abo_gp* g, const double* dXc, int64_t c_begin, int64_t m_total, int bo,
+                      double* Ks, double* pmean, int64_t mc_eff, int64_t mc, int npb) {
+    if (g->p == 1)
+        ks_build_kernel<DT, false><<<dim3(npb, (unsigned)(mc_eff / KS_CB)), 128, 0, c->stream>>>(
+            gp_spec(g), g->dXsT, g->ldx, g->n, g->N, g->Npad, g->dAlpha, dXc, c_begin, m_total, bo, Ks, pmean, mc);
+    else
+        ks_build_kernel<DT, true><<<dim3(npb, (unsigned)(mc_eff / KS_CB)), 128, 0, c->stream>>>(
+            gp_spec(g), g->dXsT, g->ldx, g->n, g->N, g->Npad, g->dAlpha, dXc, c_begin, m_total, bo, Ks, pmean, mc);
+}
+
+static double phi_prime0(int kind) {
+    if (kind == K_SE) return -0.5;
+    if (kind == K_M52 || kind == K_AM52 || kind == K_ADM52) return -5.0 / 6.0;
+    return -7.0 / 10.0;
+}
+
+// mean / var / scores for m device-resident candidates and candidate output bo; any of the
+// three outputs may be null (device pointers, length m)
+int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const double* params, double* d_mean,
+                 double* d_var, double* d_score) {
+    abo_ctx* c = g->ctx;
+    cudaStream_t st = c->stream;
+    const int64_t Npad = g->Npad;
+    const int T = (int)(Npad / NB);
+    // chunk so that the K* tile (mc x Npad doubles) stays L2-resident (~64 MB)
+    int64_t mc = ((int64_t)(64ll << 20) / (Npad * 8)) / NB * NB;
+    mc = std::max<int64_t>(NB, std::min<int64_t>(mc, 65536));
+    mc = std::min<int64_t>(mc, (m + NB - 1) / NB * NB);
+    const int64_t vpts = (Npad + g->p - 1) / g->p;                 // virtual points incl. padding columns
+    const int npb = (int)((vpts + 127) / 128);
+    double *Ks, *pmean, *sumsq;
+    int rc;
+    if ((rc = ws_get(c, WS_KS, sizeof(double) * (size_t)mc * Npad, (void**)&Ks))) return rc;
+    if ((rc = ws_get(c, WS_PMEAN, sizeof(double) * (size_t)npb * mc, (void**)&pmean))) return rc;
+    if ((rc = ws_get(c, WS_SUMSQ, sizeof(double) * (size_t)T * mc, (void**)&sumsq))) return rc;
+    AcqSpec a;
+    a.acq = acq;
+    a.p0 = params ? params[0] : 0.0;
+    a.p1 = (params && acq != ACQ_UCB && acq >= 0) ? params[1] : 0.0;
+    a.mean_c = g->mean_c[bo];
+    a.kss = (bo == 0) ? g->scale : -2.0 * g->s * g->s * g->scale * phi_prime0(g->kind);
+    for (int64_t c0 = 0; c0 < m; c0 += mc) {
+        const int64_t mvalid = std::min(mc, m - c0);
+        const int64_t mc_eff = (mvalid + NB - 1) / NB * NB;
+        const int d = g->d;
+        if (d <= 4) launch_ks<4>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
+        else if (d <= 8) launch_ks<8>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
+        else if (d <= 12) launch_ks<12>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
+        else if (d <= 16) launch_ks<16>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
+        else if (d <= 20) launch_ks<20>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
+        else if (d <= 24) launch_ks<24>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
+        else if (d <= 32) launch_ks<32>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
+        else
+            ks_build_generic_kernel<<<dim3(npb, (unsigned)(mc_eff / KS_CB)), 128, 0, st>>>(
+                gp_spec(g), g->dXsT, g->ldx, g->n, g->N, Npad, g->dAlpha, dXc, c0, m, bo, Ks, pmean, mc);
+        KL(c);
+        GemmParams p{};
+        p.A = g->dLinv; p.lda = g->ld;
+        p.B = Ks; p.ldb = Npad;
+        p.M = (int)Npad; p.N = (int)mc_eff; p.K = (int)Npad;
+        p.flags = KHI_M | REV_M;
+        p.sumsq = sumsq; p.sumsq_ld = mc;
+        CU((launch_gemm<KC, KC, EPI_SUMSQ>(p, 1, st)));
+        KL(c);
+        acq_epilogue_kernel<<<(unsigned)((mvalid + 255) / 256), 256, 0, st>>>(
+            a, pmean, npb, sumsq, T, mc, mvalid, d_mean ? d_mean + c0 : nullptr, d_var ? d_var + c0 : nullptr,
+            d_score ? d_score + c0 : nullptr);
+        KL(c);
+    }
+    CU(cudaGetLastError());
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_gp_posterior(abo_gp* g, const double* Xc, int64_t m, int32_t outputs, double* mean, double* var) {
+    if (!g || !Xc) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (!g->fitted) return abo_fail(ABO_ERR_NOT_FITTED, "surrogate has no posterior (call update first)");
+    if (outputs != 1 && outputs != g->p) return abo_fail(ABO_ERR_INVALID, "outputs must be 1 or p");
+    if (m <= 0) return ABO_OK;
+    abo_ctx* c = g->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    double *dXc, *dm, *dv;
+    int rc;
+    if ((rc = ws_get(c, WS_CAND, sizeof(double) * (size_t)m * g->d, (void**)&dXc))) return rc;
+    if ((rc = ws_get(c, WS_OUT_A, sizeof(double) * (size_t)m * outputs, (void**)&dm))) return rc;
+    if ((rc = ws_get(c, WS_OUT_B, sizeof(double) * (size_t)m * outputs, (void**)&dv))) return rc;
+    CU(cudaMemcpyAsync(dXc, Xc, sizeof(double) * m * g->d, cudaMemcpyHostToDevice, st));
+    for (int bo = 0; bo < outputs; ++bo)
+        if ((rc = sweep_device(g, dXc, m, bo, -1, nullptr, dm + (int64_t)bo * m, dv + (int64_t)bo * m, nullptr))) return rc;
+    if (mean) CU(cudaMemcpyAsync(mean, dm, sizeof(double) * m * outputs, cudaMemcpyDeviceToHost, st));
+    if (var) CU(cudaMemcpyAsync(var, dv, sizeof(double) * m * outputs, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ABO_OK;
+}
+
+// ---- stable descending top-k with Julia isless semantics (NaN largest, -0.0 < 0.0)
+static inline uint64_t ordkey(double v) {
+    if (v != v) return ~0ull;
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+void topk_host(const double* s, int64_t m, int64_t k, int64_t idx_offset, std::vector<std::pair<uint64_t, int64_t>>& heap) {
+    // heap of (key, index): the WORST kept element on top.  a is worse than b if key smaller, or
+    // equal key and larger index.
+    auto worse = [](const std::pair<uint64_t, int64_t>& a, const std::pair<uint64_t, int64_t>& b) {
+        return a.first != b.first ? a.first > b.first : a.second < b.second;   // "less" for a max-heap on badness
+    };
+    for (int64_t i = 0; i < m; ++i) {
+        std::pair<uint64_t, int64_t> e(ordkey(s[i]), i + idx_offset);
+        if ((int64_t)heap.size() < k) {
+            heap.push_back(e);
+            std::push_heap(heap.begin(), heap.end(), worse);
+        } else if (worse(e, heap.front())) {       // e is better than the current worst
+            std::pop_heap(heap.begin(), heap.end(), worse);
+            heap.back() = e;
+            std::push_heap(heap.begin(), heap.end(), worse);
+        }
+    }
+}
+
+static void topk_finish(std::vector<std::pair<uint64_t, int64_t>>& heap, const double* s, int64_t idx_offset,
+                        int64_t* top_idx, double* top_val) {
+    std::sort(heap.begin(), heap.end(), [](const std::pair<uint64_t, int64_t>& a, const std::pair<uint64_t, int64_t>& b) {
+        return a.first != b.first ? a.first > b.first : a.second < b.second;
+    });
+    for (size_t i = 0; i < heap.size(); ++i) {
+        top_idx[i] = heap[i].second;
+        top_val[i] = s[heap[i].second - idx_offset];
+    }
+}
+
+static int acq_eval_common(abo_gp* g, int acq_id, const double* params, const double* dXc, int64_t m, double* d_scores,
+                           double* h_scores, int64_t k, int64_t* top_idx, double* top_val) {
+    abo_ctx* c = g->ctx;
+    cudaStream_t st = c->stream;
+    int rc;
+    double* dS = d_scores;
+    if (!dS && (rc = ws_get(c, WS_OUT_A, sizeof(double) * (size_t)m, (void**)&dS))) return rc;
+    if ((rc = sweep_device(g, dXc, m, 0, acq_id, params, nullptr, nullptr, dS))) return rc;
+    if (h_scores || k > 0) {
+        double* hs = h_scores;
+        if (!hs) { if ((rc = pinned_get(c, sizeof(double) * (size_t)m, (void**)&hs))) return rc; }
+        CU(cudaMemcpyAsync(hs, dS, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (k > 0) {
+            std::vector<std::pair<uint64_t, int64_t>> heap;
+            heap.reserve((size_t)std::min(k, m) + 1);
+            topk_host(hs, m, std::min(k, m), 0, heap);
+            topk_finish(heap, hs, 0, top_idx, top_val);
+        }
+    } else {
+        CU(cudaStreamSynchronize(st));
+    }
+    return ABO_OK;
+}
+
+static int acq_check(abo_gp* g, int acq_id, const double* params, const void* Xc, int64_t m, int64_t k,
+                     int64_t* top_idx, double* top_val) {
+    if (!g || !Xc || !params) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (!g->fitted) return abo_fail(ABO_ERR_NOT_FITTED, "surrogate has no posterior (call update first)");
+    if (acq_id < 0 || acq_id > 2) return abo_fail(ABO_ERR_INVALID, "unknown acquisition id %d", acq_id);
+    if (m < 0 || k < 0) return abo_fail(ABO_ERR_INVALID, "negative size");
+    if (k > 0 && (!top_idx || !top_val)) return abo_fail(ABO_ERR_INVALID, "top-k buffers are NULL");
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_acq_eval(abo_gp* g, int32_t acq_id, const double* params, const double* Xc, int64_t m,
+                                double* scores, int64_t k, int64_t* top_idx, double* top_val) {
+    int rc = acq_check(g, acq_id, params, Xc, m, k, top_idx, top_val);
+    if (rc) return rc;
+    if (m == 0) return ABO_OK;
+    abo_ctx* c = g->ctx;
+    CU(cudaSetDevice(c->device));
+    double* dXc;
+    if ((rc = ws_get(c, WS_CAND, sizeof(double) * (size_t)m * g->d, (void**)&dXc))) return rc;
+    CU(cudaMemcpyAsync(dXc, Xc, sizeof(double) * m * g->d, cudaMemcpyHostToDevice, c->stream));
+    return acq_eval_common(g, acq_id, params, dXc, m, nullptr, scores, k, top_idx, top_val);
+}
+
+extern "C" int32_t abo_acq_eval_dev(abo_gp* g, int32_t acq_id, const double* params, const double* d_Xc, int64_t m,
+                                    double* d_scores, int64_t k, int64_t* top_idx, double* top_val) {
+    int rc = acq_check(g, acq_id, params, d_Xc, m, k, top_idx, top_val);
+    if (rc) return rc;
+    if (m == 0) return ABO_OK;
+    CU(cudaSetDevice(g->ctx->device));
+    return acq_eval_common(g, acq_id, params, d_Xc, m, d_scores, nullptr, k, top_idx, top_val);
+}
+
+// ------------------------------------------------------------------------------------------
+// standalone factorisation (Cholesky TFLOP/s metric)
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t abo_potrf_dev(abo_ctx* c, double* d_A, int64_t n, int64_t ld, int64_t* info) {
+    if (!c || !d_A) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (n < 1 || n % NB != 0 || ld < n || ld % 2 != 0)
+        return abo_fail(ABO_ERR_INVALID, "abo_potrf_dev needs n a multiple of 128 and an even ld >= n");
+    CU(cudaSetDevice(c->device));
+    const int T = (int)(n / NB);
+    double* Dinv; int* dinfo;
+    int rc;
+    if ((rc = ws_get(c, WS_DINV, sizeof(double) * (size_t)T * NB * NB, (void**)&Dinv))) return rc;
+    if ((rc = ws_get(c, WS_INFO, sizeof(int) * 16, (void**)&dinfo))) return rc;
+    CU(cudaMemsetAsync(dinfo, 0, sizeof(int) * 16, c->stream));
+    if ((rc = potrf_blocked(c, d_A, n, ld, 0, Dinv, 0, dinfo, 1))) return rc;
+    int hinfo = 0;
+    CU(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (info) *info = hinfo;
+    if (hinfo) return abo_fail(ABO_ERR_NOT_POSDEF, "matrix is not positive definite; Cholesky factorization failed at pivot %d", hinfo);
+    return ABO_OK;
+}

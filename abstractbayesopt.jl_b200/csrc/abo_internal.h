@@ -1,0 +1,74 @@
+// abo_internal.h — private structures shared by the translation units of libabo_cuda.so
+#pragma once
+#include <cstdint>
+#include <utility>
+#include <vector>
+#include <cuda_runtime.h>
+
+int abo_fail(int code, const char* fmt, ...);
+
+#define CU(...)                                                                                       \
+    do {                                                                                              \
+        cudaError_t e_ = (__VA_ARGS__);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            cudaGetLastError();                                                                       \
+            return abo_fail(4 /*ABO_ERR_CUDA*/, "%s failed: %s (%s:%d)", #__VA_ARGS__, cudaGetErrorString(e_), \
+                            __FILE__, __LINE__);                                                      \
+        }                                                                                             \
+    } while (0)
+
+// after every kernel launch: count it and surface launch-configuration errors
+#define KL(ctx)                                                                                       \
+    do {                                                                                              \
+        (ctx)->launches++;                                                                            \
+        cudaError_t e_ = cudaGetLastError();                                                          \
+        if (e_ != cudaSuccess)                                                                        \
+            return abo_fail(4, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+enum WsSlot {
+    WS_STAGE_X = 0, WS_STAGE_Y, WS_DINV, WS_INFO, WS_TRTRI, WS_VEC_PART, WS_KS, WS_PMEAN, WS_SUMSQ, WS_CAND,
+    WS_OUT_A, WS_OUT_B, WS_NLML_K, WS_NLML_LINV, WS_NLML_W, WS_NLML_X, WS_NLML_VEC, WS_NLML_PAR, WS_APPEND,
+    WS_TOPK, WS_COUNT
+};
+
+struct WsBuf { void* ptr = nullptr; size_t bytes = 0; };
+
+struct abo_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    WsBuf ws[WS_COUNT];
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    int64_t launches = 0;
+    // NCCL (one rank per context)
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+struct abo_gp {
+    abo_ctx* ctx = nullptr;
+    int kind = 0, d = 1, p = 1;
+    double s = 1.0, scale = 1.0, noise = 0.0;
+    std::vector<double> mean_c;
+    int64_t n = 0, N = 0, Npad = 0;      // points, system size n*p, padded to 128
+    int64_t cap_pad = 0, ld = 0, ldx = 0;
+    bool fitted = false;
+    double *dXsT = nullptr, *dL = nullptr, *dLinv = nullptr, *dAlpha = nullptr, *dBeta = nullptr,
+           *dDelta = nullptr, *dMeanC = nullptr;
+    std::vector<double> hX, hY;           // host copies of the conditioning data (ABI layout)
+};
+
+int ws_get(abo_ctx* c, int slot, size_t bytes, void** out);
+int pinned_get(abo_ctx* c, size_t bytes, void** out);
+int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strideA, double* Dinv, int64_t strideD,
+                  int* info, int batch);
+int trtri_blocked(abo_ctx* c, const double* L, double* Linv, double* W, int64_t Npad, int64_t ld, int64_t strideM,
+                  const double* Dinv, int64_t strideD, int batch);
+int solve_alpha(abo_ctx* c, const double* Linv, int64_t ld, int64_t N, const double* delta, double* beta,
+                double* alpha, int64_t strideM, int64_t strideV, int batch);
+void topk_host(const double* s, int64_t m, int64_t k, int64_t idx_offset,
+               std::vector<std::pair<uint64_t, int64_t>>& heap);
+void abo_nccl_teardown(abo_ctx* c);

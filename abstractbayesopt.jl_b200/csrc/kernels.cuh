@@ -1,0 +1,480 @@
+// kernels.cuh — the non-GEMM device code of libabo_cuda: kernel profiles, kernel-matrix
+// construction (value and derivative blocks), the 128x128 diagonal-block factor+inverse, the
+// cross-kernel K(X*, X) tile builder with fused posterior-mean partials, the acquisition
+// epilogue and a few O(n^2) vector kernels.
+//
+// Index conventions on the device
+//   system index  idx = i * p + a   (POINT-major: point i, output a; a = 0 value, a >= 1 d/dx_a)
+//   — the reference's out-major order (GradientGP.jl:919-922) only exists at the ABI.
+//   Coordinates are stored pre-scaled (s * x, ScaleTransform first — SURVEY H4) and
+//   coordinate-major:  XsT[k * ldx + i].
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace abo {
+
+constexpr int NB = 128;                 // tile / panel width everywhere
+constexpr double JITTER = 1e-18;        // AbstractGPs default_σ² (StandardGP.jl:361-379 via FiniteGP)
+
+enum KernelId { K_SE = 0, K_M52 = 1, K_M72 = 2, K_AM52 = 3, K_AM72 = 4, K_ADM52 = 5, K_ADM72 = 6 };
+enum AcqId { ACQ_EI = 0, ACQ_PI = 1, ACQ_UCB = 2 };
+
+struct KSpec {
+    int kind, d, p;
+    double s, scale, noise;
+};
+
+// phi(u), phi'(u), phi''(u), u = squared scaled distance.
+// SE: KernelFunctions SqExponentialKernel; Matern: KernelFunctions Matern52/72Kernel and
+// src/surrogates/GradientGP.jl:94-101,176-209,320-327,400-437 (Approx: Taylor branch u < 1e-10).
+__device__ __forceinline__ void phi_eval(int kind, double u, double& p, double& dp, double& ddp) {
+    if (kind == K_SE) {
+        p = exp(-u / 2);
+        dp = -p / 2;
+        ddp = p / 4;
+        return;
+    }
+    const double r = sqrt(u);
+    if (kind == K_M52 || kind == K_AM52 || kind == K_ADM52) {
+        const double q5 = 2.23606797749978969641;   // sqrt(5)
+        if (kind == K_AM52 && u < 1e-10) { p = 1.0 - (5.0 / 6.0) * u; dp = -5.0 / 6.0; ddp = 0.0; return; }
+        const double z = exp(-q5 * r);
+        p = (1 + q5 * r + 5 * u / 3) * z;
+        dp = (-5.0 / 6.0) * (1 + q5 * r) * z;
+        ddp = (25.0 / 12.0) * z;
+        return;
+    }
+    const double q7 = 2.64575131106459059050;       // sqrt(7)
+    if (kind == K_AM72 && u < 1e-10) { p = 1.0 - (7.0 / 10.0) * u; dp = -7.0 / 10.0; ddp = 0.0; return; }
+    const double z = exp(-q7 * r);
+    p = (1 + q7 * r + 14 * u / 5 + 7 * q7 * r * u / 15) * z;
+    dp = (-7.0 / 10.0) * (1 + q7 * r + 7 * u / 3) * z;
+    ddp = (49.0 / 60.0) * (1 + q7 * r) * z;
+}
+
+// gradKernel entry (src/surrogates/GradientGP.jl:573-606) in closed form; D = s*(x - y).
+//   (0,0) sig2 phi ; (a,0) 2 s sig2 phi' D_a ; (0,b) -2 s sig2 phi' D_b ;
+//   (a,b) -sig2 [ 4 s^2 phi'' D_a D_b + 2 s^2 phi' delta_ab ]
+__device__ __forceinline__ double gk_entry(const KSpec& ks, double p, double dp, double ddp, int a, int b,
+                                           double Da, double Db) {
+    if (a == 0 && b == 0) return ks.scale * p;
+    if (b == 0) return 2 * ks.s * ks.scale * dp * Da;
+    if (a == 0) return -2 * ks.s * ks.scale * dp * Db;
+    return -ks.scale * (4 * ks.s * ks.s * ddp * Da * Db + (a == b ? 2 * ks.s * ks.s * dp : 0.0));
+}
+
+// ------------------------------------------------------------------------------------------
+// coordinates:  XsT[k*ldx + i] = s * X[i*d + k]
+// ------------------------------------------------------------------------------------------
+__global__ void scale_transpose_kernel(const double* __restrict__ X, double* __restrict__ XsT, int64_t n,
+                                       int d, int64_t ldx, double s) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= ldx * d) return;
+    int k = (int)(t / ldx);
+    int64_t i = t % ldx;
+    XsT[t] = (i < n) ? s * X[i * d + k] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K + noise*I, lower tiles, identity in the padding  (StandardGP.jl:80, GradientGP.jl:662-665)
+// grid (T, T, batch); tile (blockIdx.y, blockIdx.x), skipped above the diagonal.
+// Batched form (NLML restarts): per-batch KSpec parameters come from arrays.
+// ------------------------------------------------------------------------------------------
+struct KmatBatch {
+    const double* s;       // per batch inverse lengthscale (nullptr: use spec.s)
+    const double* scale;   // per batch sigma^2
+    int64_t strideX;       // XsT stride per batch
+    int64_t strideK;
+};
+
+__global__ void __launch_bounds__(256) kmat_kernel(KSpec spec, const double* __restrict__ XsT, int64_t ldx,
+                                                   int64_t N, double* __restrict__ Kmat, int64_t ld,
+                                                   KmatBatch bt) {
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    if (bt.s) { spec.s = bt.s[blockIdx.z]; spec.scale = bt.scale[blockIdx.z]; }
+    const double* X = XsT + (int64_t)blockIdx.z * bt.strideX;
+    double* Kb = Kmat + (int64_t)blockIdx.z * bt.strideK;
+    const int c = threadIdx.x & 127;
+    const int64_t gc = (int64_t)bj * NB + c;
+    const int64_t j = gc / spec.p;
+    const int b = (int)(gc % spec.p);
+    for (int r = threadIdx.x >> 7; r < NB; r += 2) {
+        const int64_t gr = (int64_t)bi * NB + r;
+        double v;
+        if (gr >= N || gc >= N) {
+            v = (gr == gc) ? 1.0 : 0.0;
+        } else {
+            const int64_t i = gr / spec.p;
+            const int a = (int)(gr % spec.p);
+            double u = 0.0, Da = 0.0, Db = 0.0;
+            for (int k = 0; k < spec.d; ++k) {
+                double df = X[k * ldx + i] - X[k * ldx + j];
+                u = fma(df, df, u);
+                if (k == a - 1) Da = df;
+                if (k == b - 1) Db = df;
+            }
+            double p, dp, ddp;
+            phi_eval(spec.kind, u, p, dp, ddp);
+            v = gk_entry(spec, p, dp, ddp, a, b, Da, Db);
+            if (gr == gc) v += spec.noise;
+        }
+        Kb[gr * ld + gc] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 128 x 128 diagonal block:  A = L L^T in shared memory (right-looking), then L^-1 by
+// recursive doubling (8 -> 16 -> ... -> 128).  Writes L (upper part zeroed) back in place and
+// L^-1 to Dinv.  A non-positive pivot sets *info (1-based global pivot, first failure wins).
+// One CTA of 512 threads per matrix (blockIdx.x = batch).
+// ------------------------------------------------------------------------------------------
+constexpr int POTF2_LD = 129;
+constexpr int POTF2_SMEM_BYTES = (128 * POTF2_LD + 64 * 64 + 128) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(512) potf2_inv_kernel(double* __restrict__ Ablk, int64_t ld, int64_t strideA,
+                                                        double* __restrict__ Dinv, int64_t strideD,
+                                                        int* __restrict__ info, int pivot_base) {
+    extern __shared__ __align__(16) double sm[];
+    double* sL = sm;                       // [128][129]
+    double* sT = sm + 128 * POTF2_LD;      // [64*64] scratch
+    __shared__ int s_fail;
+    const int tid = threadIdx.x;
+    double* A = Ablk + (int64_t)blockIdx.x * strideA;
+    double* Di = Dinv + (int64_t)blockIdx.x * strideD;
+    if (tid == 0) s_fail = 0;
+    for (int e = tid; e < 128 * 128; e += 512) {
+        int r = e >> 7, c = e & 127;
+        sL[r * POTF2_LD + c] = A[(int64_t)r * ld + c];
+    }
+    __syncthreads();
+
+    // ---- Cholesky, right-looking, 2 barriers per column
+    for (int j = 0; j < 128; ++j) {
+        const double piv = sL[j * POTF2_LD + j];
+        if (!(piv > 0.0)) {                 // uniform: every thread reads the same value
+            if (tid == 0) { s_fail = 1; atomicCAS(info + blockIdx.x, 0, pivot_base + j + 1); }
+            break;
+        }
+        const double l = sqrt(piv);
+        const double rinv = 1.0 / l;
+        if (tid > j && tid < 128) sL[tid * POTF2_LD + j] *= rinv;
+        __syncthreads();
+        if (tid == 0) sL[j * POTF2_LD + j] = l;
+        const int t = 127 - j;              // trailing size
+        for (int e = tid; e < t * t; e += 512) {
+            int ii = e / t, cc = e - ii * t;
+            if (cc <= ii) {
+                int i = j + 1 + ii, c = j + 1 + cc;
+                sL[i * POTF2_LD + c] = fma(-sL[i * POTF2_LD + j], sL[c * POTF2_LD + j], sL[i * POTF2_LD + c]);
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    const bool failed = s_fail != 0;
+    // write L back (zero strictly-upper part so that later k-ranges may overrun the diagonal tile)
+    for (int e = tid; e < 128 * 128; e += 512) {
+        int r = e >> 7, c = e & 127;
+        A[(int64_t)r * ld + c] = (c <= r) ? sL[r * POTF2_LD + c] : 0.0;
+    }
+    if (failed) {                           // leave a harmless identity as the inverse
+        for (int e = tid; e < 128 * 128; e += 512) Di[e] = ((e >> 7) == (e & 127)) ? 1.0 : 0.0;
+        return;
+    }
+    __syncthreads();
+
+    // ---- inverse, level 0: sixteen 8x8 diagonal blocks, one thread per column
+    double x[8];
+    if (tid < 128) {
+        const int o = (tid >> 3) * 8, c = tid & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double sacc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < i && k >= c) sacc = fma(-sL[(o + i) * POTF2_LD + o + k], x[k], sacc);
+            x[i] = (i >= c) ? sacc / sL[(o + i) * POTF2_LD + o + i] : 0.0;
+        }
+    }
+    __syncthreads();
+    if (tid < 128) {
+        const int o = (tid >> 3) * 8, c = tid & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sL[(o + i) * POTF2_LD + o + c] = x[i];
+    }
+    __syncthreads();
+    // ---- levels b = 8 .. 64:  X21 = -X22 * (L21 * X11)
+    for (int b = 8; b < 128; b <<= 1) {
+        const int bb = b * b, total = 64 * b;          // (128 / 2b) pairs * b*b outputs
+        for (int e = tid; e < total; e += 512) {
+            int pair = e / bb, rem = e - pair * bb, i = rem / b, j = rem - i * b;
+            int o = pair * 2 * b;
+            const double* Lrow = sL + (o + b + i) * POTF2_LD + o;     // L21[i][k]
+            double sacc = 0.0;
+            for (int k = j; k < b; ++k) sacc = fma(Lrow[k], sL[(o + k) * POTF2_LD + o + j], sacc);
+            sT[e] = sacc;
+        }
+        __syncthreads();
+        for (int e = tid; e < total; e += 512) {
+            int pair = e / bb, rem = e - pair * bb, i = rem / b, j = rem - i * b;
+            int o = pair * 2 * b;
+            const double* Xrow = sL + (o + b + i) * POTF2_LD + o + b;  // X22[i][k]
+            const double* Tp = sT + pair * bb + j;
+            double sacc = 0.0;
+            for (int k = 0; k <= i; ++k) sacc = fma(Xrow[k], Tp[k * b], sacc);
+            sL[(o + b + i) * POTF2_LD + o + j] = -sacc;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < 128 * 128; e += 512) {
+        int r = e >> 7, c = e & 127;
+        Di[e] = (c <= r) ? sL[r * POTF2_LD + c] : 0.0;
+    }
+}
+
+// copy the T diagonal-block inverses into the diagonal tiles of Linv
+__global__ void place_diag_kernel(const double* __restrict__ Dinv, double* __restrict__ Linv, int64_t ld,
+                                  int64_t strideD, int64_t strideL) {
+    const int t = blockIdx.x;
+    const double* src = Dinv + (int64_t)blockIdx.y * strideD + (int64_t)t * NB * NB;
+    double* dst = Linv + (int64_t)blockIdx.y * strideL + (int64_t)t * NB * (ld + 1);
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) dst[(int64_t)(e >> 7) * ld + (e & 127)] = src[e];
+}
+
+// ------------------------------------------------------------------------------------------
+// O(n^2) vector kernels on row-major lower-triangular matrices
+// ------------------------------------------------------------------------------------------
+// out[r] = sum_{k <= r} T[r][k] * v[k]        one warp per row, fixed-order reduction
+__global__ void trmv_lower_kernel(const double* __restrict__ T, int64_t ld, int64_t N,
+                                  const double* __restrict__ v, double* __restrict__ out, int64_t strideT,
+                                  int64_t strideV) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= N) return;
+    const double* row = T + (int64_t)blockIdx.y * strideT + r * ld;
+    const double* vv = v + (int64_t)blockIdx.y * strideV;
+    double s = 0.0;
+    for (int64_t k = lane; k <= r; k += 32) s = fma(row[k], vv[k], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[(int64_t)blockIdx.y * strideV + r] = s;
+}
+
+// part[chunk][j] = sum_{i in chunk, i >= j} T[i][j] * v[i]     (T^T v, two-stage, deterministic)
+constexpr int TRMVT_ROWS = 256;
+__global__ void trmvT_lower_partial_kernel(const double* __restrict__ T, int64_t ld, int64_t N,
+                                           const double* __restrict__ v, double* __restrict__ part,
+                                           int64_t strideT, int64_t strideV, int64_t strideP) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.y * TRMVT_ROWS;
+    if (j >= N) return;
+    const double* Tb = T + (int64_t)blockIdx.z * strideT;
+    const double* vv = v + (int64_t)blockIdx.z * strideV;
+    int64_t i1 = i0 + TRMVT_ROWS; if (i1 > N) i1 = N;
+    double s = 0.0;
+    for (int64_t i = (i0 > j ? i0 : j); i < i1; ++i) s = fma(Tb[i * ld + j], vv[i], s);
+    part[(int64_t)blockIdx.z * strideP + (int64_t)blockIdx.y * N + j] = s;
+}
+__global__ void reduce_rows_kernel(const double* __restrict__ part, int nchunks, int64_t N,
+                                   double* __restrict__ out, int64_t strideP, int64_t strideO) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += part[(int64_t)blockIdx.y * strideP + (int64_t)c * N + j];
+    out[(int64_t)blockIdx.y * strideO + j] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// cross-kernel tile builder:  Ks[c][idx] = gradKernel((x_i, a), (x*_c, bo))  for a chunk of
+// candidates, K-contiguous (row per candidate, ld = Npad), zeros in the padding columns, plus
+// the posterior-mean partials  pmean[point-block][c] = sum_{idx in block} Ks[c][idx]*alpha[idx]
+// (StandardGP.jl:361-363: mean = m(x*) + K*^T alpha).
+// Thread = training point (coordinates in registers), CTA loops over KS_CB candidates held in
+// shared memory.  grid (point blocks of 128, candidate blocks).
+// bo = candidate output (0 = value: posterior_mean/var; b >= 1: posterior_grad_*).
+// ------------------------------------------------------------------------------------------
+constexpr int KS_CB = 32;
+
+template <int DT, bool GRAD>
+__global__ void __launch_bounds__(128) ks_build_kernel(KSpec spec, const double* __restrict__ XsT, int64_t ldx,
+                                                       int64_t npts, int64_t N, int64_t Npad,
+                                                       const double* __restrict__ alpha,
+                                                       const double* __restrict__ Xc, int64_t c_begin,
+                                                       int64_t m_total, int bo, double* __restrict__ Ks,
+                                                       double* __restrict__ pmean, int64_t mc) {
+    __shared__ double sc[KS_CB][DT];
+    __shared__ double swsum[4][KS_CB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t i = blockIdx.x * 128LL + tid;            // training point
+    const int64_t cb0 = (int64_t)blockIdx.y * KS_CB;       // first candidate of this CTA (chunk-local)
+    for (int e = tid; e < KS_CB * DT; e += 128) {
+        int c = e / DT, k = e - c * DT;
+        int64_t gc = c_begin + cb0 + c;
+        sc[c][k] = (k < spec.d && gc < m_total) ? spec.s * Xc[gc * spec.d + k] : 0.0;
+    }
+    double x[DT];
+#pragma unroll
+    for (int k = 0; k < DT; ++k) x[k] = (k < spec.d && i < npts) ? XsT[k * ldx + i] : 0.0;
+    const int p = spec.p;
+    const int64_t idx0 = i * p;
+    const double al0 = (!GRAD && i < npts) ? alpha[idx0] : 0.0;
+    __syncthreads();
+    for (int c = 0; c < KS_CB; ++c) {
+        double u = 0.0, Db = 0.0;
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            double df = x[k] - sc[c][k];
+            u = fma(df, df, u);
+            if (k == bo - 1) Db = df;
+        }
+        double contrib = 0.0;
+        double* row = Ks + (cb0 + c) * Npad;
+        if (i < npts) {
+            double ph, dph, ddph;
+            phi_eval(spec.kind, u, ph, dph, ddph);
+            if (!GRAD) {
+                double v = gk_entry(spec, ph, dph, ddph, 0, bo, 0.0, Db);
+                row[idx0] = v;
+                contrib = v * al0;
+            } else {
+                for (int a = 0; a < p; ++a) {
+                    // D_a re-read through L1 (keeps x[] in registers: no dynamic indexing)
+                    double Da = (a == 0) ? 0.0 : XsT[(a - 1) * ldx + i] - sc[c][a - 1];
+                    double v = gk_entry(spec, ph, dph, ddph, a, bo, Da, Db);
+                    row[idx0 + a] = v;
+                    contrib = fma(v, alpha[idx0 + a], contrib);
+                }
+            }
+        } else {
+            for (int a = 0; a < p; ++a)
+                if (idx0 + a < Npad) row[idx0 + a] = 0.0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        if (lane == 0) swsum[warp][c] = contrib;
+    }
+    __syncthreads();
+    if (tid < KS_CB)
+        pmean[(int64_t)blockIdx.x * mc + cb0 + tid] = ((swsum[0][tid] + swsum[1][tid]) + swsum[2][tid]) + swsum[3][tid];
+}
+
+// generic-d fallback (d > 32): coordinates re-read from global memory
+__global__ void __launch_bounds__(128) ks_build_generic_kernel(KSpec spec, const double* __restrict__ XsT,
+                                                               int64_t ldx, int64_t npts, int64_t N, int64_t Npad,
+                                                               const double* __restrict__ alpha,
+                                                               const double* __restrict__ Xc, int64_t c_begin,
+                                                               int64_t m_total, int bo, double* __restrict__ Ks,
+                                                               double* __restrict__ pmean, int64_t mc) {
+    __shared__ double swsum[4][KS_CB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t i = blockIdx.x * 128LL + tid;
+    const int64_t cb0 = (int64_t)blockIdx.y * KS_CB;
+    const int p = spec.p;
+    const int64_t idx0 = i * p;
+    for (int c = 0; c < KS_CB; ++c) {
+        const int64_t gc = c_begin + cb0 + c;
+        double contrib = 0.0;
+        double* row = Ks + (cb0 + c) * Npad;
+        if (i < npts) {
+            double u = 0.0, Db = 0.0;
+            for (int k = 0; k < spec.d; ++k) {
+                double ck = (gc < m_total) ? spec.s * Xc[gc * spec.d + k] : 0.0;
+                double df = XsT[k * ldx + i] - ck;
+                u = fma(df, df, u);
+                if (k == bo - 1) Db = df;
+            }
+            double ph, dph, ddph;
+            phi_eval(spec.kind, u, ph, dph, ddph);
+            for (int a = 0; a < p; ++a) {
+                double Da = 0.0;
+                if (a > 0) {
+                    double ck = (gc < m_total) ? spec.s * Xc[gc * spec.d + a - 1] : 0.0;
+                    Da = XsT[(a - 1) * ldx + i] - ck;
+                }
+                double v = gk_entry(spec, ph, dph, ddph, a, bo, Da, Db);
+                row[idx0 + a] = v;
+                contrib = fma(v, alpha[idx0 + a], contrib);
+            }
+        } else {
+            for (int a = 0; a < p; ++a)
+                if (idx0 + a < Npad) row[idx0 + a] = 0.0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        if (lane == 0) swsum[warp][c] = contrib;
+    }
+    __syncthreads();
+    if (tid < KS_CB)
+        pmean[(int64_t)blockIdx.x * mc + cb0 + tid] = ((swsum[0][tid] + swsum[1][tid]) + swsum[2][tid]) + swsum[3][tid];
+}
+
+// ------------------------------------------------------------------------------------------
+// acquisition epilogue: mean, variance, EI / PI / UCB  for one chunk of candidates
+//   mean = m + sum_blocks pmean ; var = (k** - sum_tiles sumsq) + 1e-18
+//   EI  (ExpectedImprovement.jl:40-66), PI (ProbabilityImprovement.jl:38-63),
+//   UCB (UpperConfidenceBound.jl:38-45) — same operation order as the reference.
+// ------------------------------------------------------------------------------------------
+struct AcqSpec {
+    int acq;            // -1: posterior only
+    double p0, p1;      // EI/PI: xi, best_y ; UCB: beta
+    double mean_c;      // prior mean of the queried output
+    double kss;         // prior variance of the queried output
+};
+
+__device__ __forceinline__ double normcdf_ref(double z) { return erfc(-z * 0.70710678118654752440) / 2; }
+__device__ __forceinline__ double normpdf_ref(double z) { return exp(-(z * z) / 2) * 0.39894228040143267794; }
+
+__device__ __forceinline__ double acq_value(const AcqSpec& a, double mu, double var) {
+    if (a.acq == ACQ_UCB) return -mu + a.p0 * sqrt(fmax(var, 0.0));
+    const double delta = (a.p1 - a.p0) - mu;
+    if (var <= 1e-12) return fmax(delta, 0.0);
+    const double sig = sqrt(var);
+    const double z = delta / sig;
+    if (a.acq == ACQ_EI) return delta * normcdf_ref(z) + sig * normpdf_ref(z);
+    return normcdf_ref(z);
+}
+
+__global__ void acq_epilogue_kernel(AcqSpec a, const double* __restrict__ pmean, int npb,
+                                    const double* __restrict__ sumsq, int ntile, int64_t mc, int64_t mvalid,
+                                    double* __restrict__ mean_out, double* __restrict__ var_out,
+                                    double* __restrict__ score_out) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= mvalid) return;
+    double mu = 0.0;
+    for (int b = 0; b < npb; ++b) mu += pmean[(int64_t)b * mc + c];
+    mu += a.mean_c;
+    double q = 0.0;
+    for (int t = 0; t < ntile; ++t) q += sumsq[(int64_t)t * mc + c];
+    const double var = (a.kss - q) + JITTER;
+    if (mean_out) mean_out[c] = mu;
+    if (var_out) var_out[c] = var;
+    if (score_out && a.acq >= 0) score_out[c] = acq_value(a, mu, var);
+}
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+// delta (point-major) from y (out-major at the ABI):  delta[i*p + a] = y[a*n + i] - mean_c[a]
+__global__ void delta_kernel(const double* __restrict__ y, const double* __restrict__ mean_c, int64_t n, int p,
+                             double* __restrict__ delta) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * p) return;
+    const int64_t i = t / p;
+    const int a = (int)(t % p);
+    delta[t] = y[(int64_t)a * n + i] - mean_c[a];
+}
+// out-major <- point-major permutation of a length n*p vector
+__global__ void to_out_major_kernel(const double* __restrict__ v, int64_t n, int p, double* __restrict__ out) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * p) return;
+    out[(t % p) * n + t / p] = v[t];
+}
+__global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) p[t] = v;
+}
+
+}  // namespace abo

@@ -1,0 +1,136 @@
+/* abo.h — C ABI of libabo_cuda.so: the B200-native GP-surrogate + acquisition hot path of
+ * AbstractBayesOpt.jl (reference paths below are relative to the reference repository).
+ *
+ * There is no FFI in the reference (it is pure Julia on AbstractGPs/KernelFunctions); these
+ * entry points are what new `AbstractSurrogate` / `AbstractAcquisition` subtypes bind with
+ * `ccall` so that `BOStruct` / `optimize` (src/bayesian_opt.jl:364-449) run unchanged.
+ * See INTEGRATION.md for the Julia-side stubs.
+ *
+ * Conventions
+ *  - every function returns an abo_status (0 = OK); all floating data is double;
+ *  - host matrices are "point-major": X[i*d + k] is coordinate k of point i — the memory of a
+ *    Julia d x n column-major Matrix{Float64} (reduce(hcat, xs)) or a NumPy (n, d) C array;
+ *  - GradientGP observations / multi-output results are OUT-MAJOR, idx = out*n + i, exactly
+ *    prep_output (src/surrogates/GradientGP.jl:919-922);
+ *  - indices returned to the caller are 0-based int64 (the Julia shim adds 1);
+ *  - pointers named d_* are DEVICE pointers (on the context's device), everything else is
+ *    host memory owned by the caller; the library never keeps a host pointer after return;
+ *  - calls are synchronous: results are in the caller's buffers when the function returns.
+ *  - no CPU fallback: every entry point fails with ABO_ERR_CUDA when no device is usable.
+ */
+#ifndef ABO_H
+#define ABO_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct abo_ctx abo_ctx;   /* one CUDA device + stream + workspace (+ optional NCCL rank) */
+typedef struct abo_gp abo_gp;     /* a conditioned surrogate resident in HBM */
+
+typedef enum {
+    ABO_OK = 0,
+    ABO_ERR_INVALID = 1,       /* bad argument (ArgumentError) */
+    ABO_ERR_DIM = 2,           /* DimensionMismatch (test/test_bayesian_opt.jl:788-817) */
+    ABO_ERR_NOT_POSDEF = 3,    /* LinearAlgebra.PosDefException(info) (src/bayesian_opt.jl:126-141) */
+    ABO_ERR_CUDA = 4,          /* CUDA runtime failure / no device */
+    ABO_ERR_NOT_FITTED = 5,    /* posterior queried before update() */
+    ABO_ERR_NCCL = 6,
+    ABO_ERR_ALLOC = 7
+} abo_status;
+
+/* base kernels: KernelFunctions SqExponentialKernel / Matern52Kernel / Matern72Kernel and the
+ * in-repo ApproxMatern / ADMatern kernels (src/surrogates/GradientGP.jl:52-101,133-249,278-327,356-474) */
+typedef enum {
+    ABO_KERNEL_SE = 0, ABO_KERNEL_MATERN52 = 1, ABO_KERNEL_MATERN72 = 2,
+    ABO_KERNEL_APPROX_MATERN52 = 3, ABO_KERNEL_APPROX_MATERN72 = 4,
+    ABO_KERNEL_AD_MATERN52 = 5, ABO_KERNEL_AD_MATERN72 = 6
+} abo_kernel;
+
+/* acquisition functions (src/acquisition_functions/{ExpectedImprovement,ProbabilityImprovement,
+ * UpperConfidenceBound}.jl).  params: EI/PI = {xi, best_y}; UCB = {beta}. */
+typedef enum { ABO_ACQ_EI = 0, ABO_ACQ_PI = 1, ABO_ACQ_UCB = 2 } abo_acq;
+
+int32_t abo_version(void);
+const char* abo_last_error(void);          /* thread-local message of the last failure */
+
+/* ---- context ------------------------------------------------------------------------- */
+int32_t abo_ctx_create(int32_t device, abo_ctx** out);
+int32_t abo_ctx_destroy(abo_ctx* ctx);
+int32_t abo_ctx_device(const abo_ctx* ctx, int32_t* device);
+/* cudaStream_t the context launches on (for callers that time with events on that stream) */
+int32_t abo_ctx_stream(const abo_ctx* ctx, void** stream);
+/* number of kernels this context has launched so far (bench.py "gpu_launches") */
+int32_t abo_ctx_launch_count(const abo_ctx* ctx, int64_t* count);
+
+/* ---- surrogate: struct StandardGP / GradientGP (src/surrogates/StandardGP.jl:11-16,
+ *      GradientGP.jl:17-22).  p = 1 (StandardGP) or d + 1 (GradientGP). --------------------- */
+int32_t abo_gp_create(abo_ctx* ctx, int32_t kernel_id, int32_t d, int32_t p, abo_gp** out);
+int32_t abo_gp_destroy(abo_gp* gp);
+/* inv_lengthscale is the stored ScaleTransform s = 1/l (surrogates_utils.jl:28-47), scale is the
+ * ScaledKernel sigma^2, noise_var the observation noise, mean_c[p] the constant prior mean per
+ * output (NULL = ZeroMean).  Invalidates any posterior held by the handle. */
+int32_t abo_gp_set_params(abo_gp* gp, double inv_lengthscale, double scale, double noise_var,
+                          const double* mean_c);
+/* update(model, xs, ys) (StandardGP.jl:79-83, GradientGP.jl:659-668): K + noise*I, Cholesky,
+ * alpha.  *info = 0, or the 1-based failing pivot in the caller's out-major ordering is NOT
+ * guaranteed — only info > 0 is (status ABO_ERR_NOT_POSDEF); the handle is then un-fitted. */
+int32_t abo_gp_fit(abo_gp* gp, const double* X, const double* y, int64_t n, int64_t* info);
+/* O(n^2) row append of one observation (x[d], y[p]); transactional: on ABO_ERR_NOT_POSDEF the
+ * handle still holds the previous posterior.  (The reference re-fits: bayesian_opt.jl:125.) */
+int32_t abo_gp_append(abo_gp* gp, const double* x, const double* y, int64_t* info);
+/* Base.copy(::StandardGP) (StandardGP.jl:26, surrogates_utils.jl:12-14): deep copy on device */
+int32_t abo_gp_clone(const abo_gp* gp, abo_gp** out);
+int32_t abo_gp_n(const abo_gp* gp, int64_t* n);
+/* read back alpha (N = n*p, out-major) — PosteriorGP.data.α */
+int32_t abo_gp_alpha(const abo_gp* gp, double* alpha);
+
+/* read back the Cholesky factor (which = 0: lower L with K + noise*I = L L^T — the transpose of
+ * PosteriorGP.data.C.U) or its inverse (which = 1) as a dense N x N row-major matrix in the
+ * library's internal POINT-major ordering idx = i*p + out.  Inspection / tests only. */
+int32_t abo_gp_factor(const abo_gp* gp, int32_t which, double* out);
+
+/* posterior_mean / posterior_var (StandardGP.jl:361-379, GradientGP.jl:985-1003) when
+ * outputs == 1; posterior_grad_mean / posterior_grad_var (GradientGP.jl:936-955) when
+ * outputs == p (results out-major, length m*p).  mean / var may each be NULL. */
+int32_t abo_gp_posterior(abo_gp* gp, const double* Xc, int64_t m, int32_t outputs,
+                         double* mean, double* var);
+
+/* fused acquisition sweep: scores = acq(surrogate, Xc) (ExpectedImprovement.jl:40-45 etc.) and
+ * sortperm(scores; rev=true)[1:k] (acq_utils.jl:50-52): stable, descending, NaN first.
+ * scores (m) may be NULL; k may be 0 (top_idx/top_val then unused). */
+int32_t abo_acq_eval(abo_gp* gp, int32_t acq_id, const double* params, const double* Xc, int64_t m,
+                     double* scores, int64_t k, int64_t* top_idx, double* top_val);
+/* same, candidates already resident in HBM (d_Xc: m*d doubles, point-major); d_scores (device,
+ * m doubles) may be NULL.  top_idx/top_val are host buffers. */
+int32_t abo_acq_eval_dev(abo_gp* gp, int32_t acq_id, const double* params, const double* d_Xc,
+                         int64_t m, double* d_scores, int64_t k, int64_t* top_idx, double* top_val);
+
+/* nlml(model, [log l, log sig2], xs, ys) and its gradient for R parameter vectors at once
+ * (StandardGP.jl:99-149, GradientGP.jl:684-738, driven by bayesian_opt.jl:259-300).
+ * logparams: R x 2 (row r = {log l, log sig2}); nlml: R; grad: R x 2 (may be NULL);
+ * info: R (0 or failing pivot; a failed restart has nlml = +Inf, like the skipped restarts of
+ * bayesian_opt.jl:296-299).  Uses gp's kernel id, noise and prior mean; does not touch its
+ * posterior. */
+int32_t abo_nlml_batch(abo_gp* gp, const double* X, const double* y, int64_t n,
+                       const double* logparams, int64_t R, double* nlml, double* grad, int32_t* info);
+
+/* ---- standalone factorisation entry (Cholesky TFLOP/s metric; A is n x n row-major, lower
+ *      triangle referenced, overwritten by L on device; d_A device pointer, ld >= n) ---------- */
+int32_t abo_potrf_dev(abo_ctx* ctx, double* d_A, int64_t n, int64_t ld, int64_t* info);
+
+/* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------------------- */
+int32_t abo_nccl_unique_id(uint8_t id[128]);
+int32_t abo_ctx_init_rank(abo_ctx* ctx, int32_t rank, int32_t nranks, const uint8_t id[128]);
+/* broadcast the posterior (X, L, L^-1, alpha, hyper-parameters) from `root` to every rank */
+int32_t abo_gp_sync(abo_gp* gp, int32_t root);
+/* all-gather every rank's (value, global index) top-k lists and merge them with the
+ * (value desc, index asc, NaN first) order; in/out arrays have length k (count valid entries) */
+int32_t abo_topk_allgather(abo_ctx* ctx, int64_t k, int64_t count, int64_t* top_idx, double* top_val,
+                           int64_t* out_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABO_H */
