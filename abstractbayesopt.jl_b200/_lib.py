@@ -16,7 +16,7 @@ ABO_OK, ABO_ERR_INVALID, ABO_ERR_DIM, ABO_ERR_NOT_POSDEF, ABO_ERR_CUDA, ABO_ERR_
 # every symbol include/abo.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "abo_version", "abo_last_error", "abo_ctx_create", "abo_ctx_destroy", "abo_ctx_device", "abo_ctx_stream",
-    "abo_ctx_launch_count", "abo_gp_create", "abo_gp_destroy", "abo_gp_set_params", "abo_gp_fit", "abo_gp_append",
+    "abo_ctx_launch_count", "abo_ctx_profile", "abo_ctx_profile_read", "abo_gp_create", "abo_gp_destroy", "abo_gp_set_params", "abo_gp_fit", "abo_gp_append",
     "abo_gp_clone", "abo_gp_n", "abo_gp_alpha", "abo_gp_factor", "abo_gp_posterior", "abo_acq_eval", "abo_acq_eval_dev",
     "abo_nlml_batch", "abo_potrf_dev", "abo_nccl_unique_id", "abo_ctx_init_rank", "abo_gp_sync",
     "abo_topk_allgather",
@@ -61,6 +61,8 @@ def lib():
             "abo_ctx_device": [vp, C.POINTER(i32)],
             "abo_ctx_stream": [vp, C.POINTER(vp)],
             "abo_ctx_launch_count": [vp, C.POINTER(i64)],
+            "abo_ctx_profile": [vp, i32],
+            "abo_ctx_profile_read": [vp, vp, vp],
             "abo_gp_create": [vp, i32, i32, i32, C.POINTER(vp)],
             "abo_gp_destroy": [vp],
             "abo_gp_set_params": [vp, dbl, dbl, dbl, vp],
@@ -131,6 +133,14 @@ class Context:
         n = C.c_int64()
         check(lib().abo_ctx_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def profile(self, enable: bool):
+        check(lib().abo_ctx_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        ms = (C.c_double * 3)(); n = (C.c_int64 * 3)()
+        check(lib().abo_ctx_profile_read(self._h, ms, n))
+        return list(ms), list(n)
 
     def potrf_dev(self, dptr: int, n: int, ld: int) -> int:
         info = C.c_int64(0)

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include <new>
 #include <string>
@@ -16,6 +17,7 @@
 #include "../../include/abo.h"
 #include "gemm_dmma.cuh"
 #include "kernels.cuh"
+#include "sweep_tma.cuh"
 #include "abo_internal.h"
 
 using namespace abo;
@@ -47,6 +49,7 @@ static int configure_kernels() {
     CU(configure_gemm<MC, MC, EPI_STORE>());
     CU(configure_gemm<KC, KC, EPI_SUMSQ>());
     CU(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(sweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
     return ABO_OK;
 }
 
@@ -83,6 +86,7 @@ extern "C" int32_t abo_ctx_destroy(abo_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& b : c->ws) if (b.ptr) cudaFree(b.ptr);
+    for (auto e : c->prof_events) cudaEventDestroy(e);
     if (c->pinned) cudaFreeHost(c->pinned);
     abo_nccl_teardown(c);
     cudaEventDestroy(c->ev_a);
@@ -106,6 +110,78 @@ extern "C" int32_t abo_ctx_stream(const abo_ctx* c, void** stream) {
 extern "C" int32_t abo_ctx_launch_count(const abo_ctx* c, int64_t* count) {
     if (!c || !count) return abo_fail(ABO_ERR_INVALID, "null argument");
     *count = c->launches;
+    return ABO_OK;
+}
+
+// ---- per-kernel sweep timing --------------------------------------------------------------
+int prof_mark(abo_ctx* c) {          // record the next event of the (start, stop) x 3 classes sequence
+    if (!c->profile) return ABO_OK;
+    if (c->prof_used == c->prof_events.size()) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        c->prof_events.push_back(e);
+    }
+    CU(cudaEventRecord(c->prof_events[c->prof_used++], c->stream));
+    return ABO_OK;
+}
+int prof_collect(abo_ctx* c) {       // after a stream sync: fold the recorded pairs into the totals
+    if (!c->profile) return ABO_OK;
+    for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]));
+        int cls = (int)((i / 2) % 3);
+        c->prof_ms[cls] += ms;
+        c->prof_n[cls] += 1;
+    }
+    c->prof_used = 0;
+    return ABO_OK;
+}
+extern "C" int32_t abo_ctx_profile(abo_ctx* c, int32_t enable) {
+    if (!c) return abo_fail(ABO_ERR_INVALID, "null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->profile = enable != 0;
+    c->prof_used = 0;
+    for (int i = 0; i < 3; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    return ABO_OK;
+}
+extern "C" int32_t abo_ctx_profile_read(abo_ctx* c, double ms[3], int64_t launches[3]) {
+    if (!c || !ms || !launches) return abo_fail(ABO_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    int rc = prof_collect(c);
+    if (rc) return rc;
+    for (int i = 0; i < 3; ++i) { ms[i] = c->prof_ms[i]; launches[i] = c->prof_n[i]; }
+    return ABO_OK;
+}
+
+// ---- TMA tensor maps (driver entry point fetched through the runtime: no -lcuda link) --------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+// row-major matrix [rows][K] of doubles with leading dimension ld; box = 4 (k) x 128 (rows)
+int make_tmap_k4(CUtensorMap* map, const double* base, int64_t K, int64_t rows, int64_t ld) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return abo_fail(ABO_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+    cuuint32_t box[2] = {4, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return abo_fail(ABO_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return ABO_OK;
 }
 
@@ -464,8 +540,16 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
     cudaStream_t st = c->stream;
     const int64_t Npad = g->Npad;
     const int T = (int)(Npad / NB);
-    // chunk so that the K* tile (mc x Npad doubles) stays L2-resident (~64 MB)
-    int64_t mc = ((int64_t)(64ll << 20) / (Npad * 8)) / NB * NB;
+    // chunk: enough tiles per launch (>= ~2048) that the persistent kernel's tail is small, K* buffer
+    // bounded by 512 MB.  (v1 kernel, ABO_SWEEP_V1=1: L2-resident 64 MB chunks.)
+    static const bool use_v1 = getenv("ABO_SWEEP_V1") != nullptr;
+    int64_t mc;
+    if (use_v1) {
+        mc = ((int64_t)(64ll << 20) / (Npad * 8)) / NB * NB;
+    } else {
+        mc = (int64_t)NB * ((2048 + T - 1) / T);
+        mc = std::min<int64_t>(mc, ((int64_t)(512ll << 20) / (Npad * 8)) / NB * NB);
+    }
     mc = std::max<int64_t>(NB, std::min<int64_t>(mc, 65536));
     mc = std::min<int64_t>(mc, (m + NB - 1) / NB * NB);
     const int64_t vpts = (Npad + g->p - 1) / g->p;                 // virtual points incl. padding columns
@@ -475,6 +559,11 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
     if ((rc = ws_get(c, WS_KS, sizeof(double) * (size_t)mc * Npad, (void**)&Ks))) return rc;
     if ((rc = ws_get(c, WS_PMEAN, sizeof(double) * (size_t)npb * mc, (void**)&pmean))) return rc;
     if ((rc = ws_get(c, WS_SUMSQ, sizeof(double) * (size_t)T * mc, (void**)&sumsq))) return rc;
+    CUtensorMap tmA, tmB;
+    if (!use_v1) {
+        if ((rc = make_tmap_k4(&tmA, g->dLinv, Npad, Npad, g->ld))) return rc;
+        if ((rc = make_tmap_k4(&tmB, Ks, Npad, mc, Npad))) return rc;
+    }
     AcqSpec a;
     a.acq = acq;
     a.p0 = params ? params[0] : 0.0;
@@ -485,6 +574,7 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
         const int64_t mvalid = std::min(mc, m - c0);
         const int64_t mc_eff = (mvalid + NB - 1) / NB * NB;
         const int d = g->d;
+        if ((rc = prof_mark(c))) return rc;
         if (d <= 4) launch_ks<4>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
         else if (d <= 8) launch_ks<8>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
         else if (d <= 12) launch_ks<12>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
@@ -496,18 +586,34 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
             ks_build_generic_kernel<<<dim3(npb, (unsigned)(mc_eff / KS_CB)), 128, 0, st>>>(
                 gp_spec(g), g->dXsT, g->ldx, g->n, g->N, Npad, g->dAlpha, dXc, c0, m, bo, Ks, pmean, mc);
         KL(c);
-        GemmParams p{};
-        p.A = g->dLinv; p.lda = g->ld;
-        p.B = Ks; p.ldb = Npad;
-        p.M = (int)Npad; p.N = (int)mc_eff; p.K = (int)Npad;
-        p.flags = KHI_M | REV_M;
-        p.sumsq = sumsq; p.sumsq_ld = mc;
-        CU((launch_gemm<KC, KC, EPI_SUMSQ>(p, 1, st)));
+        if ((rc = prof_mark(c))) return rc;
+        if ((rc = prof_mark(c))) return rc;
+        if (use_v1) {
+            GemmParams p{};
+            p.A = g->dLinv; p.lda = g->ld;
+            p.B = Ks; p.ldb = Npad;
+            p.M = (int)Npad; p.N = (int)mc_eff; p.K = (int)Npad;
+            p.flags = KHI_M | REV_M;
+            p.sumsq = sumsq; p.sumsq_ld = mc;
+            CU((launch_gemm<KC, KC, EPI_SUMSQ>(p, 1, st)));
+        } else {
+            SweepParams sp;
+            sp.T = T; sp.ncb = (int)(mc_eff / NB); sp.sumsq = sumsq; sp.sumsq_ld = mc;
+            const int grid = std::min(c->sms, sp.T * sp.ncb);
+            sweep_tma_kernel<<<grid, SW_THREADS, SW_SMEM_BYTES, st>>>(tmA, tmB, sp);
+        }
         KL(c);
+        if ((rc = prof_mark(c))) return rc;
+        if ((rc = prof_mark(c))) return rc;
         acq_epilogue_kernel<<<(unsigned)((mvalid + 255) / 256), 256, 0, st>>>(
             a, pmean, npb, sumsq, T, mc, mvalid, d_mean ? d_mean + c0 : nullptr, d_var ? d_var + c0 : nullptr,
             d_score ? d_score + c0 : nullptr);
         KL(c);
+        if ((rc = prof_mark(c))) return rc;
+        if (c->profile && c->prof_used >= 6 * 512) {       // bound the event pool
+            CU(cudaStreamSynchronize(st));
+            if ((rc = prof_collect(c))) return rc;
+        }
     }
     CU(cudaGetLastError());
     return ABO_OK;

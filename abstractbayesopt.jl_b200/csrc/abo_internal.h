@@ -43,6 +43,12 @@ struct abo_ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     int64_t launches = 0;
+    // optional per-kernel timing of the sweep (abo_ctx_profile)
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;     // pairs, class = (index / 2) % 3
+    size_t prof_used = 0;
+    double prof_ms[3] = {0, 0, 0};
+    int64_t prof_n[3] = {0, 0, 0};
     // NCCL (one rank per context)
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
@@ -72,3 +78,5 @@ int solve_alpha(abo_ctx* c, const double* Linv, int64_t ld, int64_t N, const dou
 void topk_host(const double* s, int64_t m, int64_t k, int64_t idx_offset,
                std::vector<std::pair<uint64_t, int64_t>>& heap);
 void abo_nccl_teardown(abo_ctx* c);
+int prof_mark(abo_ctx* c);
+int prof_collect(abo_ctx* c);

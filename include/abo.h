@@ -64,6 +64,13 @@ int32_t abo_ctx_stream(const abo_ctx* ctx, void** stream);
 /* number of kernels this context has launched so far (bench.py "gpu_launches") */
 int32_t abo_ctx_launch_count(const abo_ctx* ctx, int64_t* count);
 
+/* per-kernel device timing of the candidate sweep (CUDA events on the context's stream around
+ * every launch; bench.py's roofline leg).  enable != 0 resets and starts collecting; read
+ * returns accumulated milliseconds and launch counts for {K* tile builder, DMMA triangular
+ * product + sum-of-squares, acquisition epilogue}. */
+int32_t abo_ctx_profile(abo_ctx* ctx, int32_t enable);
+int32_t abo_ctx_profile_read(abo_ctx* ctx, double ms[3], int64_t launches[3]);
+
 /* ---- surrogate: struct StandardGP / GradientGP (src/surrogates/StandardGP.jl:11-16,
  *      GradientGP.jl:17-22).  p = 1 (StandardGP) or d + 1 (GradientGP). --------------------- */
 int32_t abo_gp_create(abo_ctx* ctx, int32_t kernel_id, int32_t d, int32_t p, abo_gp** out);
