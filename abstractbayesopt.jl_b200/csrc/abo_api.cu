@@ -48,8 +48,10 @@ static int configure_kernels() {
     CU(configure_gemm<KC, MC, EPI_STORE>());
     CU(configure_gemm<MC, MC, EPI_STORE>());
     CU(configure_gemm<KC, KC, EPI_SUMSQ>());
+    CU(cudaFuncSetAttribute(gemm64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G64_SMEM_BYTES));
     CU(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM_BYTES));
     CU(cudaFuncSetAttribute(sweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
     return ABO_OK;
 }
 
@@ -71,8 +73,10 @@ extern "C" int32_t abo_ctx_create(int32_t device, abo_ctx** out) {
     if (!c) return abo_fail(ABO_ERR_ALLOC, "host allocation failed");
     c->device = device;
     c->sms = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));    // main / panel stream
+    CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));   // look-ahead trailing updates
     CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
     int rc = configure_kernels();
@@ -242,6 +246,76 @@ int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strid
         CU((launch_gemm<KC, KC, EPI_STORE>(s, batch, st)));   // A_22 -= L_21 L_21^T
         KL(c);
     }
+    return ABO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Single-matrix Cholesky with two-level blocking and look-ahead (the "Cholesky TFLOP/s" path).
+//   outer block = OB tile columns (512): inside it the panels are factored right-looking
+//   (potf2+inverse, TRSM-as-GEMM, SYRK restricted to the block's own columns, K = 128);
+//   the rest of the trailing matrix is updated ONCE per outer block with K = 512 by the
+//   TMA/mbarrier DMMA kernel (syrk_tma_kernel), split into
+//       U_next : the next outer block's columns  -> panel stream (high priority)
+//       U_rest : everything further right        -> second stream, overlaps the next panel
+// ------------------------------------------------------------------------------------------
+int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Dinv, int* info) {
+    const int T = (int)(Npad / NB);
+    const int OB = 4;
+    if (T <= OB) return potrf_blocked(c, A, Npad, ld, 0, Dinv, 0, info, 1);
+    cudaStream_t sp = c->stream, su = c->stream2;
+    CUtensorMap tmL;
+    int rc = make_tmap_k4(&tmL, A, Npad, Npad, ld);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_a, sp));                 // su must see everything enqueued on sp so far
+    CU(cudaStreamWaitEvent(su, c->ev_a, 0));
+    bool rest_pending = false;
+    for (int Jb = 0; Jb < T; Jb += OB) {
+        const int je = std::min(Jb + OB, T);
+        // ---- panel block: tile columns [Jb, je)
+        for (int jp = Jb; jp < je; ++jp) {
+            double* Ajj = A + (int64_t)jp * NB * (ld + 1);
+            double* Dj = Dinv + (int64_t)jp * NB * NB;
+            potf2_inv_kernel<<<1, 512, POTF2_SMEM_BYTES, sp>>>(Ajj, ld, 0, Dj, 0, info, jp * NB);
+            KL(c);
+            const int rem = (T - jp - 1) * NB;
+            if (rem <= 0) break;
+            double* P = Ajj + (int64_t)NB * ld;
+            GemmParams g{};
+            g.A = P; g.lda = ld; g.B = Dj; g.ldb = NB; g.C = P; g.ldc = ld;
+            g.M = rem; g.N = NB; g.K = NB; g.alpha = 1.0; g.beta = 0.0; g.flags = 0;
+            CU(launch_gemm64(g, 1, sp));
+            KL(c);
+            const int ncol = (je - jp - 1) * NB;       // remaining columns of this outer block
+            if (ncol > 0) {
+                GemmParams s{};
+                s.A = P; s.lda = ld; s.B = P; s.ldb = ld;
+                s.C = Ajj + (int64_t)NB * (ld + 1); s.ldc = ld;
+                s.M = rem; s.N = ncol; s.K = NB; s.alpha = -1.0; s.beta = 1.0; s.flags = LOWER_ONLY;
+                CU(launch_gemm64(s, 1, sp));
+                KL(c);
+            }
+        }
+        if (je >= T) break;
+        SyrkParams u;
+        u.C = A; u.ld = ld; u.kcol0 = Jb * NB; u.nk = (je - Jb) * (NB / 16);
+        // ---- U_rest(b) on the second stream: needs panel(b) (event) and, by stream order, U_rest(b-1)
+        const int jn = std::min(je + OB, T);
+        CU(cudaEventRecord(c->ev_a, sp));
+        if (jn < T) {
+            CU(cudaStreamWaitEvent(su, c->ev_a, 0));
+            u.row_t0 = jn; u.col_t0 = jn;
+            syrk_tma_kernel<<<dim3(T - jn, T - jn), SW_THREADS, SW_SMEM_BYTES, su>>>(tmL, u);
+            KL(c);
+        }
+        // ---- U_next(b) on the panel stream: the next block's columns; they were last touched by
+        //      U_rest(b-1), so wait for it
+        if (rest_pending) CU(cudaStreamWaitEvent(sp, c->ev_b, 0));
+        u.row_t0 = je; u.col_t0 = je;
+        syrk_tma_kernel<<<dim3(jn - je, T - je), SW_THREADS, SW_SMEM_BYTES, sp>>>(tmL, u);
+        KL(c);
+        if (jn < T) { CU(cudaEventRecord(c->ev_b, su)); rest_pending = true; }
+    }
+    if (rest_pending) CU(cudaStreamWaitEvent(sp, c->ev_b, 0));
     return ABO_OK;
 }
 
@@ -439,7 +513,7 @@ extern "C" int32_t abo_gp_fit(abo_gp* g, const double* X, const double* y, int64
     if ((rc = ws_get(c, WS_INFO, sizeof(int) * 16, (void**)&dinfo))) return rc;
     if ((rc = ws_get(c, WS_TRTRI, sizeof(double) * (size_t)Npad * Npad, (void**)&W))) return rc;
     CU(cudaMemsetAsync(dinfo, 0, sizeof(int) * 16, st));
-    if ((rc = potrf_blocked(c, g->dL, Npad, g->ld, 0, Dinv, 0, dinfo, 1))) return rc;
+    if ((rc = potrf_lookahead(c, g->dL, Npad, g->ld, Dinv, dinfo))) return rc;
     int hinfo = 0;
     CU(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -750,7 +824,7 @@ extern "C" int32_t abo_potrf_dev(abo_ctx* c, double* d_A, int64_t n, int64_t ld,
     if ((rc = ws_get(c, WS_DINV, sizeof(double) * (size_t)T * NB * NB, (void**)&Dinv))) return rc;
     if ((rc = ws_get(c, WS_INFO, sizeof(int) * 16, (void**)&dinfo))) return rc;
     CU(cudaMemsetAsync(dinfo, 0, sizeof(int) * 16, c->stream));
-    if ((rc = potrf_blocked(c, d_A, n, ld, 0, Dinv, 0, dinfo, 1))) return rc;
+    if ((rc = potrf_lookahead(c, d_A, n, ld, Dinv, dinfo))) return rc;
     int hinfo = 0;
     CU(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

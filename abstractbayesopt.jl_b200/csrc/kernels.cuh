@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include "gemm_dmma.cuh"
+
 namespace abo {
 
 constexpr int NB = 128;                 // tile / panel width everywhere
@@ -132,16 +134,19 @@ __global__ void __launch_bounds__(256) kmat_kernel(KSpec spec, const double* __r
 // One CTA of 512 threads per matrix (blockIdx.x = batch).
 // ------------------------------------------------------------------------------------------
 constexpr int POTF2_LD = 129;
-constexpr int POTF2_SMEM_BYTES = (128 * POTF2_LD + 64 * 64 + 128) * (int)sizeof(double);
+constexpr int POTF2_PLD = 132;                                   // sub-panel buffer [32][132]
+constexpr int POTF2_SCRATCH = 64 * 68;                           // >= 32*132 and >= 64*(b+4) for b <= 64
+constexpr int POTF2_SMEM_BYTES = (128 * POTF2_LD + POTF2_SCRATCH + 16) * (int)sizeof(double);
 
 __global__ void __launch_bounds__(512) potf2_inv_kernel(double* __restrict__ Ablk, int64_t ld, int64_t strideA,
                                                         double* __restrict__ Dinv, int64_t strideD,
                                                         int* __restrict__ info, int pivot_base) {
     extern __shared__ __align__(16) double sm[];
     double* sL = sm;                       // [128][129]
-    double* sT = sm + 128 * POTF2_LD;      // [64*64] scratch
+    double* sT = sm + 128 * POTF2_LD;      // scratch: sub-panel columns, then T of the inverse levels
     __shared__ int s_fail;
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
     double* A = Ablk + (int64_t)blockIdx.x * strideA;
     double* Di = Dinv + (int64_t)blockIdx.x * strideD;
     if (tid == 0) s_fail = 0;
@@ -151,25 +156,81 @@ __global__ void __launch_bounds__(512) potf2_inv_kernel(double* __restrict__ Abl
     }
     __syncthreads();
 
-    // ---- Cholesky, right-looking, 2 barriers per column
-    for (int j = 0; j < 128; ++j) {
-        const double piv = sL[j * POTF2_LD + j];
-        if (!(piv > 0.0)) {                 // uniform: every thread reads the same value
-            if (tid == 0) { s_fail = 1; atomicCAS(info + blockIdx.x, 0, pivot_base + j + 1); }
-            break;
-        }
-        const double l = sqrt(piv);
-        const double rinv = 1.0 / l;
-        if (tid > j && tid < 128) sL[tid * POTF2_LD + j] *= rinv;
-        __syncthreads();
-        if (tid == 0) sL[j * POTF2_LD + j] = l;
-        const int t = 127 - j;              // trailing size
-        for (int e = tid; e < t * t; e += 512) {
-            int ii = e / t, cc = e - ii * t;
-            if (cc <= ii) {
-                int i = j + 1 + ii, c = j + 1 + cc;
-                sL[i * POTF2_LD + c] = fma(-sL[i * POTF2_LD + j], sL[c * POTF2_LD + j], sL[i * POTF2_LD + c]);
+    // ---- Cholesky: four 32-column sub-panels.  Column step j (one barrier): every thread reads
+    // the pivot and the still-unscaled column j, forms l_ij = a_ij / sqrt(piv) itself (its own
+    // row i and the <= 31 sub-panel rows c it needs), updates its part of row i inside the
+    // sub-panel and parks l_ij in the panel buffer; the scaled columns are written back to sL
+    // after the sub-panel, followed by a DMMA update of the rest of the block.
+    bool bad = false;
+    for (int sp = 0; sp < 4 && !bad; ++sp) {
+        const int c0 = sp * 32, c1 = c0 + 32;
+        const int i = tid & 127, cq = tid >> 7;               // row, column phase (0..3)
+        for (int j = c0; j < c1; ++j) {
+            const double piv = sL[j * POTF2_LD + j];
+            if (!(piv > 0.0)) {                                 // uniform: same value in every thread
+                if (tid == 0) { s_fail = 1; atomicCAS(info + blockIdx.x, 0, pivot_base + j + 1); }
+                bad = true;
+                break;
             }
+            const double rinv = rsqrt(piv);
+            const double aij = sL[i * POTF2_LD + j];
+            const double lij = (i == j) ? piv * rinv : aij * rinv;
+            double lc[8], v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int c = j + 1 + cq + 4 * q;
+                const bool on = (c < c1) && (i >= c);
+                lc[q] = on ? sL[c * POTF2_LD + j] : 0.0;
+                v[q] = on ? sL[i * POTF2_LD + c] : 0.0;
+            }
+            if (cq == 0 && i >= j) sT[(j - c0) * POTF2_PLD + i] = lij;
+            // no hazard inside a step: it reads column j and its own row, and writes only its own
+            // row in columns > j; the single barrier below orders these writes against the next
+            // step's reads of column j + 1
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int c = j + 1 + cq + 4 * q;
+                if ((c < c1) && (i >= c)) sL[i * POTF2_LD + c] = fma(-lij, lc[q] * rinv, v[q]);
+            }
+            __syncthreads();
+        }
+        if (bad) break;
+        // scaled sub-panel columns back into sL (rows >= column)
+        for (int e = tid; e < 32 * 128; e += 512) {
+            const int cc = e >> 7, r = e & 127;
+            if (r >= c0 + cc) sL[r * POTF2_LD + c0 + cc] = sT[cc * POTF2_PLD + r];
+        }
+        __syncthreads();
+        if (c1 >= 128) break;
+        // trailing update of rows/cols >= c1 with the panel columns [c0, c1): lower 16x16 tiles
+        const int nt = (128 - c1) / 16;
+        const int ntile = nt * (nt + 1) / 2;
+        for (int t = warp; t < ntile; t += 16) {
+            int ti = 0, acc_t = t;
+            while (acc_t > ti) { acc_t -= ti + 1; ++ti; }
+            const int tj = acc_t;
+            const int r0 = c1 + 16 * ti, q0 = c1 + 16 * tj;
+            double cacc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                double a[2], b[2];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) a[mi] = sT[(4 * kk + fk) * POTF2_PLD + r0 + 8 * mi + fr];
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) b[ni] = sT[(4 * kk + fk) * POTF2_PLD + q0 + 8 * ni + fr];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni) dmma8x8x4(cacc[mi][ni][0], cacc[mi][ni][1], a[mi], b[ni]);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {
+                    double* dst = sL + (r0 + 8 * mi + fr) * POTF2_LD + q0 + 8 * ni + 2 * fk;
+                    dst[0] -= cacc[mi][ni][0];
+                    dst[1] -= cacc[mi][ni][1];
+                }
         }
         __syncthreads();
     }
@@ -206,26 +267,39 @@ __global__ void __launch_bounds__(512) potf2_inv_kernel(double* __restrict__ Abl
         for (int i = 0; i < 8; ++i) sL[(o + i) * POTF2_LD + o + c] = x[i];
     }
     __syncthreads();
-    // ---- levels b = 8 .. 64:  X21 = -X22 * (L21 * X11)
+    // ---- levels b = 8 .. 64:  X21 = -X22 * (L21 * X11), both products as DMMA 8x8 tiles that
+    //      skip the structurally zero k-ranges; T is staged in scratch with row stride b + 4.
     for (int b = 8; b < 128; b <<= 1) {
-        const int bb = b * b, total = 64 * b;          // (128 / 2b) pairs * b*b outputs
-        for (int e = tid; e < total; e += 512) {
-            int pair = e / bb, rem = e - pair * bb, i = rem / b, j = rem - i * b;
-            int o = pair * 2 * b;
-            const double* Lrow = sL + (o + b + i) * POTF2_LD + o;     // L21[i][k]
-            double sacc = 0.0;
-            for (int k = j; k < b; ++k) sacc = fma(Lrow[k], sL[(o + k) * POTF2_LD + o + j], sacc);
-            sT[e] = sacc;
+        const int tb = b >> 3;                           // 8x8 tiles per block side
+        const int tpp = tb * tb;                         // tiles per pair
+        const int ntl = (64 / b) * tpp;                  // tiles over all pairs
+        const int ST = b + 4;
+        for (int t = warp; t < ntl; t += 16) {
+            const int pair = t / tpp, rem = t - pair * tpp, ti = rem / tb, tj = rem - ti * tb;
+            const int o = pair * 2 * b;
+            double c0a = 0.0, c1a = 0.0;
+            for (int k = tj * 8; k < b; k += 4) {        // X11[k][n] = 0 for k < n
+                const double a = sL[(o + b + ti * 8 + fr) * POTF2_LD + o + k + fk];
+                const double bv = sL[(o + k + fk) * POTF2_LD + o + tj * 8 + fr];
+                dmma8x8x4(c0a, c1a, a, bv);
+            }
+            double* dst = sT + pair * b * ST + (ti * 8 + fr) * ST + tj * 8 + 2 * fk;
+            dst[0] = c0a;
+            dst[1] = c1a;
         }
         __syncthreads();
-        for (int e = tid; e < total; e += 512) {
-            int pair = e / bb, rem = e - pair * bb, i = rem / b, j = rem - i * b;
-            int o = pair * 2 * b;
-            const double* Xrow = sL + (o + b + i) * POTF2_LD + o + b;  // X22[i][k]
-            const double* Tp = sT + pair * bb + j;
-            double sacc = 0.0;
-            for (int k = 0; k <= i; ++k) sacc = fma(Xrow[k], Tp[k * b], sacc);
-            sL[(o + b + i) * POTF2_LD + o + j] = -sacc;
+        for (int t = warp; t < ntl; t += 16) {
+            const int pair = t / tpp, rem = t - pair * tpp, ti = rem / tb, tj = rem - ti * tb;
+            const int o = pair * 2 * b;
+            double c0a = 0.0, c1a = 0.0;
+            for (int k = 0; k < (ti + 1) * 8; k += 4) {  // X22[m][k] = 0 for k > m
+                const double a = sL[(o + b + ti * 8 + fr) * POTF2_LD + o + b + k + fk];
+                const double bv = sT[pair * b * ST + (k + fk) * ST + tj * 8 + fr];
+                dmma8x8x4(c0a, c1a, a, bv);
+            }
+            double* dst = sL + (o + b + ti * 8 + fr) * POTF2_LD + o + tj * 8 + 2 * fk;
+            dst[0] = -c0a;
+            dst[1] = -c1a;
         }
         __syncthreads();
     }

@@ -183,4 +183,111 @@ sweep_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Trailing update of the blocked Cholesky with the same TMA / mbarrier / DMMA pipeline:
+//     C[i-tile, j-tile] -= L[i rows, kcol0 : kcol0 + 16*nk] * L[j rows, same columns]^T
+// for the lower tiles (j <= i) of a rectangular range of tiles.  One tile per CTA (not
+// persistent) so that the higher-priority panel stream of the look-ahead schedule can slip its
+// small kernels in between tiles.  A and B are both K-contiguous row panels of the SAME
+// row-major matrix, hence one tensor map.
+// ------------------------------------------------------------------------------------------
+struct SyrkParams {
+    double* C;          // base of the matrix (row-major, ld)
+    int64_t ld;
+    int row_t0, col_t0; // first row tile / column tile of this launch's grid
+    int kcol0;          // first column of the panel block
+    int nk;             // k16 steps (panel width / 16)
+};
+
+__global__ void __launch_bounds__(SW_THREADS, 1)
+syrk_tma_kernel(const __grid_constant__ CUtensorMap tmL, SyrkParams p) {
+    extern __shared__ __align__(128) unsigned char sw_smem[];
+    double* stage_base = reinterpret_cast<double*>(sw_smem);
+    uint64_t* full = reinterpret_cast<uint64_t*>(sw_smem + SW_STAGES * SW_STAGE_BYTES + 4 * 128 * 8);
+    uint64_t* empty = full + SW_STAGES;
+    const int it = p.row_t0 + blockIdx.y, jt = p.col_t0 + blockIdx.x;
+    if (jt > it) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = it * 128, n0 = jt * 128;
+
+    if (tid == 0) {
+        for (int s = 0; s < SW_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kt = 0; kt < p.nk; ++kt) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], SW_STAGE_BYTES);
+                double* sa = stage_base + (size_t)stage * (2 * SW_OPER_DOUBLES);
+                double* sb = sa + SW_OPER_DOUBLES;
+                const int k0 = p.kcol0 + kt * 16;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    tma_load_2d(sa + q * 512, &tmL, k0 + 4 * q, m0, &full[stage]);
+                    tma_load_2d(sb + q * 512, &tmL, k0 + 4 * q, n0, &full[stage]);
+                }
+                if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
+    const int fr = lane >> 2, fk = lane & 3;
+    int stage = 0;
+    uint32_t phase = 0;
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    for (int kt = 0; kt < p.nk; ++kt) {
+        mbar_wait(&full[stage], phase);
+        const double* a_s = stage_base + (size_t)stage * (2 * SW_OPER_DOUBLES) + ((wm + fr) << 2) + fk;
+        const double* b_s = stage_base + (size_t)stage * (2 * SW_OPER_DOUBLES) + SW_OPER_DOUBLES + ((wn + fr) << 2) + fk;
+        double a[2][4], bb[2][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[0][i] = a_s[i * 32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bb[0][j] = b_s[j * 32];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int cur = kk & 1, nxt = cur ^ 1;
+            if (kk < 3) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[nxt][i] = a_s[(kk + 1) * 512 + i * 32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bb[nxt][j] = b_s[(kk + 1) * 512 + j * 32];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[cur][i], bb[cur][j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = m0 + wm + i * 8 + fr;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = n0 + wn + j * 8 + 2 * fk;
+            double2* dst = reinterpret_cast<double2*>(p.C + (int64_t)row * p.ld + col);
+            double2 o = *dst;
+            o.x -= acc[i][j][0];
+            o.y -= acc[i][j][1];
+            *dst = o;
+        }
+    }
+}
+
 }  // namespace abo

@@ -54,6 +54,8 @@ def extract_scale_and_lengthscale(kernel: Kernel):
 
 def normalized(kernel: Kernel) -> Kernel:
     """What StandardGP(kernel, …) stores: always Scaled(Transformed(base)) (StandardGP.jl:47-59)."""
+    if kernel.inv_lengthscale is not None and kernel.scale is not None:
+        return kernel                      # already Scaled(Transformed(base)): the prior is shared, not rebuilt
     inner, scale, ls = extract_scale_and_lengthscale(kernel)
     inner = with_lengthscale(inner, 1.0 if ls is None else ls)
     return replace(inner, scale=scale)

@@ -198,7 +198,7 @@ def test_gradient_gp_known_answer(abo, orc):
 def test_potrf_dev(abo):
     import torch
     ctx = abo.default_context()
-    for n in (128, 640, 1024):
+    for n in (128, 640, 1024, 2176):
         g = torch.Generator(device="cpu").manual_seed(n)
         A = torch.randn(n, n, dtype=torch.float64, generator=g)
         A = A @ A.T / n + torch.eye(n, dtype=torch.float64)
