@@ -202,6 +202,11 @@ int ws_get(abo_ctx* c, int slot, size_t bytes, void** out) {
     return ABO_OK;
 }
 
+void ws_release(abo_ctx* c, int slot) {
+    auto& b = c->ws[slot];
+    if (b.ptr) { cudaStreamSynchronize(c->stream); cudaFree(b.ptr); b.ptr = nullptr; b.bytes = 0; }
+}
+
 int pinned_get(abo_ctx* c, size_t bytes, void** out) {
     if (c->pinned_bytes < bytes) {
         if (c->pinned) { CU(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->pinned); c->pinned = nullptr; c->pinned_bytes = 0; }
@@ -409,7 +414,7 @@ static void gp_free_device(abo_gp* g) {
     g->cap_pad = 0;
 }
 
-static int gp_alloc(abo_gp* g, int64_t Npad, int64_t ldx) {
+int gp_alloc(abo_gp* g, int64_t Npad, int64_t ldx) {
     gp_free_device(g);
     size_t mat = sizeof(double) * (size_t)Npad * Npad;
     cudaError_t e;
@@ -716,12 +721,6 @@ extern "C" int32_t abo_gp_posterior(abo_gp* g, const double* Xc, int64_t m, int3
 }
 
 // ---- stable descending top-k with Julia isless semantics (NaN largest, -0.0 < 0.0)
-static inline uint64_t ordkey(double v) {
-    if (v != v) return ~0ull;
-    uint64_t u;
-    memcpy(&u, &v, 8);
-    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-}
 
 void topk_host(const double* s, int64_t m, int64_t k, int64_t idx_offset, std::vector<std::pair<uint64_t, int64_t>>& heap) {
     // heap of (key, index): the WORST kept element on top.  a is worse than b if key smaller, or
@@ -832,3 +831,5 @@ extern "C" int32_t abo_potrf_dev(abo_ctx* c, double* d_A, int64_t n, int64_t ld,
     if (hinfo) return abo_fail(ABO_ERR_NOT_POSDEF, "matrix is not positive definite; Cholesky factorization failed at pivot %d", hinfo);
     return ABO_OK;
 }
+
+#include "abo_extra.cuh"

@@ -1,0 +1,237 @@
+// abo_extra.cuh — O(n^2) row append and the batched NLML (+ analytic gradient) entry points.
+// Included at the end of abo_api.cu (one translation unit owns every __global__ definition).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/abo.h"
+#include "gemm_dmma.cuh"
+#include "kernels.cuh"
+#include "abo_internal.h"
+
+using namespace abo;
+
+static KSpec spec_of(const abo_gp* g) {
+    KSpec k;
+    k.kind = g->kind; k.d = g->d; k.p = g->p; k.s = g->s; k.scale = g->scale; k.noise = g->noise;
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------
+// abo_gp_append — one new observation, O(n^2):
+//   w = L^-1 k(X, x)           (TRMV, reads L^-1 once)
+//   pivot = k(x,x) + noise - |w|^2   -> not positive: ABO_ERR_NOT_POSDEF, state untouched
+//   L[n,:] = [w, sqrt(pivot)] ;  L^-1[n,:] = [-(L^-T w)/l, 1/l]   (second pass over L^-1)
+//   beta_n, alpha += L^-1[n,:]^T beta_n
+// The reference has no such path (it re-fits, src/bayesian_opt.jl:125); the result equals a
+// re-fit up to rounding (the GPU tests compare it with a full re-fit).
+// ------------------------------------------------------------------------------------------
+static int grow_capacity(abo_gp* g) {
+    abo_ctx* c = g->ctx;
+    cudaStream_t st = c->stream;
+    const int64_t old_pad = g->cap_pad, new_pad = old_pad + NB;
+    double *nL = nullptr, *nLinv = nullptr, *nA = nullptr, *nB = nullptr, *nD = nullptr;
+    size_t mat = sizeof(double) * (size_t)new_pad * new_pad;
+    cudaError_t e;
+    if ((e = cudaMalloc(&nL, mat)) != cudaSuccess || (e = cudaMalloc(&nLinv, mat)) != cudaSuccess ||
+        (e = cudaMalloc(&nA, sizeof(double) * new_pad)) != cudaSuccess ||
+        (e = cudaMalloc(&nB, sizeof(double) * new_pad)) != cudaSuccess ||
+        (e = cudaMalloc(&nD, sizeof(double) * new_pad)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(nL); cudaFree(nLinv); cudaFree(nA); cudaFree(nB); cudaFree(nD);
+        return abo_fail(ABO_ERR_ALLOC, "growing the posterior to %lld rows failed: %s", (long long)new_pad, cudaGetErrorString(e));
+    }
+    const int64_t tot = new_pad * new_pad;
+    grow_matrix_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g->dL, old_pad, g->ld, nL, new_pad);
+    KL(c);
+    grow_matrix_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g->dLinv, old_pad, g->ld, nLinv, new_pad);
+    KL(c);
+    CU(cudaMemsetAsync(nA, 0, sizeof(double) * new_pad, st));
+    CU(cudaMemsetAsync(nB, 0, sizeof(double) * new_pad, st));
+    CU(cudaMemsetAsync(nD, 0, sizeof(double) * new_pad, st));
+    CU(cudaMemcpyAsync(nA, g->dAlpha, sizeof(double) * old_pad, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(nB, g->dBeta, sizeof(double) * old_pad, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(nD, g->dDelta, sizeof(double) * old_pad, cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(g->dL); cudaFree(g->dLinv); cudaFree(g->dAlpha); cudaFree(g->dBeta); cudaFree(g->dDelta);
+    g->dL = nL; g->dLinv = nLinv; g->dAlpha = nA; g->dBeta = nB; g->dDelta = nD;
+    g->cap_pad = new_pad; g->ld = new_pad; g->Npad = new_pad;
+    return ABO_OK;
+}
+
+static int grow_points(abo_gp* g) {
+    abo_ctx* c = g->ctx;
+    const int64_t new_ldx = g->ldx + 4 * NB;
+    double* nX = nullptr;
+    cudaError_t e = cudaMalloc(&nX, sizeof(double) * (size_t)new_ldx * g->d);
+    if (e != cudaSuccess) { cudaGetLastError(); return abo_fail(ABO_ERR_ALLOC, "growing the coordinate store failed"); }
+    CU(cudaMemsetAsync(nX, 0, sizeof(double) * new_ldx * g->d, c->stream));
+    CU(cudaMemcpy2DAsync(nX, sizeof(double) * new_ldx, g->dXsT, sizeof(double) * g->ldx, sizeof(double) * g->ldx, g->d,
+                         cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(g->dXsT);
+    g->dXsT = nX; g->ldx = new_ldx;
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_gp_append(abo_gp* g, const double* x, const double* y, int64_t* info_out) {
+    if (!g || !x || !y) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (!g->fitted) return abo_fail(ABO_ERR_NOT_FITTED, "append needs a fitted surrogate (call abo_gp_fit first)");
+    if (g->p != 1)
+        return abo_fail(ABO_ERR_INVALID, "abo_gp_append supports StandardGP (p = 1); re-fit a GradientGP");
+    abo_ctx* c = g->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int64_t n = g->n;
+    int rc;
+    // scratch: xnew[d] | kv[Npad] | w[Npad] | r[Npad] | ss[1]
+    const int64_t Np = g->Npad;
+    double* buf;
+    if ((rc = ws_get(c, WS_APPEND, sizeof(double) * (size_t)(g->d + 3 * Np + 8), (void**)&buf))) return rc;
+    double *dx = buf, *kv = buf + g->d, *w = kv + Np, *r = w + Np, *ss = r + Np;
+    CU(cudaMemcpyAsync(dx, x, sizeof(double) * g->d, cudaMemcpyHostToDevice, st));
+    kvec_kernel<<<(unsigned)((Np + 255) / 256), 256, 0, st>>>(spec_of(g), g->dXsT, g->ldx, n, Np, dx, kv);
+    KL(c);
+    {
+        dim3 grid((unsigned)((n * 32 + 255) / 256), 1);
+        trmv_lower_kernel<<<grid, 256, 0, st>>>(g->dLinv, g->ld, n, kv, w, 0, 0);
+        KL(c);
+    }
+    sumsq_vec_kernel<<<1, 1024, 0, st>>>(w, n, ss);
+    KL(c);
+    double hss = 0.0;
+    CU(cudaMemcpyAsync(&hss, ss, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const double piv = (g->scale + g->noise) - hss;          // k(x,x) = sig2 * phi(0) = sig2
+    if (!(piv > 0.0)) {
+        if (info_out) *info_out = n + 1;
+        return abo_fail(ABO_ERR_NOT_POSDEF, "matrix is not positive definite; Cholesky factorization failed at pivot %lld",
+                        (long long)(n + 1));
+    }
+    if (info_out) *info_out = 0;
+    const double l = std::sqrt(piv);
+    // r = Linv^T w over rows 0..n-1
+    const int nchunks = (int)((n + TRMVT_ROWS - 1) / TRMVT_ROWS);
+    double* part;
+    if ((rc = ws_get(c, WS_VEC_PART, sizeof(double) * (size_t)nchunks * n, (void**)&part))) return rc;
+    {
+        dim3 grid((unsigned)((n + 127) / 128), nchunks, 1);
+        trmvT_lower_partial_kernel<<<grid, 128, 0, st>>>(g->dLinv, g->ld, n, w, part, 0, 0, 0);
+        KL(c);
+        reduce_rows_kernel<<<dim3((unsigned)((n + 127) / 128), 1), 128, 0, st>>>(part, nchunks, n, r, 0, 0);
+        KL(c);
+    }
+    if (n + 1 > g->cap_pad) {                 // no padding row left: one more tile
+        if ((rc = grow_capacity(g))) return rc;
+    }
+    if (n + 1 > g->ldx) { if ((rc = grow_points(g))) return rc; }
+    append_commit_kernel<<<1, 1024, 0, st>>>(g->dL, g->dLinv, g->ld, n, w, r, l, y[0] - g->mean_c[0], g->dDelta, g->dBeta,
+                                             g->dAlpha, g->dXsT, g->ldx, dx, g->d, g->s);
+    KL(c);
+    CU(cudaStreamSynchronize(st));
+    g->n = n + 1; g->N = n + 1;
+    g->hX.insert(g->hX.end(), x, x + g->d);
+    g->hY.push_back(y[0]);
+    return ABO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// abo_nlml_batch — R hyper-parameter vectors in lock-step:
+//   K_b + noise I (batched kmat) -> batched blocked Cholesky -> batched triangular inverse ->
+//   beta_b, alpha_b -> Cinv_b = Linv_b^T Linv_b (DMMA, structurally-zero k skipped) ->
+//   fused reduction  sum (Cinv - alpha alpha^T) .* dK/dtheta  with dK recomputed from X.
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, int64_t n, const double* logparams,
+                                  int64_t R, double* nlml, double* grad, int32_t* info) {
+    if (!g || !X || !y || !logparams || !nlml) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (n < 1) return abo_fail(ABO_ERR_DIM, "need at least one observation");
+    if (R <= 0) return ABO_OK;
+    abo_ctx* c = g->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int d = g->d, p = g->p;
+    const int64_t N = n * p, Npad = (N + NB - 1) / NB * NB, ldx = (n + NB - 1) / NB * NB;
+    const int T = (int)(Npad / NB);
+    const size_t mat = sizeof(double) * (size_t)Npad * Npad;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = std::min<size_t>((size_t)24 << 30, free_b / 2);
+    int64_t Rc = std::max<int64_t>(1, std::min<int64_t>(R, (int64_t)(budget / (3 * mat))));
+    int rc;
+    double *Kb, *Linv, *W, *Xb, *vec, *par, *Dinv, *dXraw, *dYraw;
+    int* dinfo;
+    if ((rc = ws_get(c, WS_NLML_K, mat * Rc, (void**)&Kb))) return rc;
+    if ((rc = ws_get(c, WS_NLML_LINV, mat * Rc, (void**)&Linv))) return rc;
+    if ((rc = ws_get(c, WS_NLML_W, mat * Rc, (void**)&W))) return rc;
+    if ((rc = ws_get(c, WS_NLML_X, sizeof(double) * (size_t)Rc * ldx * d, (void**)&Xb))) return rc;
+    // vec: delta[Rc][Npad] | beta | alpha | out[Rc][3]
+    if ((rc = ws_get(c, WS_NLML_VEC, sizeof(double) * (size_t)Rc * (3 * Npad + 4), (void**)&vec))) return rc;
+    // par: s[Rc] | scale[Rc] | tile partials [Rc][T*T][2]
+    if ((rc = ws_get(c, WS_NLML_PAR, sizeof(double) * (size_t)Rc * (2 + 2 * (size_t)T * T), (void**)&par))) return rc;
+    if ((rc = ws_get(c, WS_DINV, sizeof(double) * (size_t)Rc * T * NB * NB, (void**)&Dinv))) return rc;
+    if ((rc = ws_get(c, WS_INFO, sizeof(int) * std::max<int64_t>(16, Rc), (void**)&dinfo))) return rc;
+    if ((rc = ws_get(c, WS_STAGE_X, sizeof(double) * (size_t)n * d, (void**)&dXraw))) return rc;
+    if ((rc = ws_get(c, WS_STAGE_Y, sizeof(double) * (size_t)(N + p), (void**)&dYraw))) return rc;
+    double *delta = vec, *beta = vec + Rc * Npad, *alpha = beta + Rc * Npad, *out = alpha + Rc * Npad;
+    double *sb = par, *scb = par + Rc, *tpart = par + 2 * Rc;
+    CU(cudaMemcpyAsync(dXraw, X, sizeof(double) * n * d, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dYraw, y, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dYraw + N, g->mean_c.data(), sizeof(double) * p, cudaMemcpyHostToDevice, st));
+    std::vector<double> hs(Rc), hsc(Rc), hout(3 * Rc);
+    std::vector<int> hinfo(Rc);
+    KSpec spec = spec_of(g);
+    for (int64_t r0 = 0; r0 < R; r0 += Rc) {
+        const int nb = (int)std::min<int64_t>(Rc, R - r0);
+        for (int b = 0; b < nb; ++b) {
+            hs[b] = std::exp(-logparams[2 * (r0 + b)]);           // s = 1 / l
+            hsc[b] = std::exp(logparams[2 * (r0 + b) + 1]);
+        }
+        CU(cudaMemcpyAsync(sb, hs.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(scb, hsc.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(dinfo, 0, sizeof(int) * nb, st));
+        CU(cudaMemsetAsync(delta, 0, sizeof(double) * (size_t)nb * Npad, st));
+        {
+            int64_t tot = ldx * d;
+            scale_transpose_batched_kernel<<<dim3((unsigned)((tot + 255) / 256), nb), 256, 0, st>>>(dXraw, Xb, n, d, ldx, sb);
+            KL(c);
+            for (int b = 0; b < nb; ++b) {
+                delta_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(dYraw, dYraw + N, n, p, delta + (int64_t)b * Npad);
+                KL(c);
+            }
+        }
+        KmatBatch bt{sb, scb, ldx * d, Npad * Npad};
+        kmat_kernel<<<dim3(T, T, nb), 256, 0, st>>>(spec, Xb, ldx, N, Kb, Npad, bt);
+        KL(c);
+        if ((rc = potrf_blocked(c, Kb, Npad, Npad, Npad * Npad, Dinv, (int64_t)T * NB * NB, dinfo, nb))) return rc;
+        if ((rc = trtri_blocked(c, Kb, Linv, W, Npad, Npad, Npad * Npad, Dinv, (int64_t)T * NB * NB, nb))) return rc;
+        if ((rc = solve_alpha(c, Linv, Npad, Npad, delta, beta, alpha, Npad * Npad, Npad, nb))) return rc;
+        if (grad) {
+            GemmParams q{};                                        // Cinv = Linv^T Linv, lower tiles, k >= m
+            q.A = Linv; q.B = Linv; q.C = W;
+            q.lda = q.ldb = q.ldc = Npad; q.strideA = q.strideB = q.strideC = Npad * Npad;
+            q.M = q.N = q.K = (int)Npad; q.alpha = 1.0; q.beta = 0.0; q.flags = KLO_M | LOWER_ONLY;
+            CU((launch_gemm<MC, MC, EPI_STORE>(q, nb, st)));
+            KL(c);
+            nlml_grad_tile_kernel<<<dim3(T, T, nb), 256, 0, st>>>(spec, bt, Xb, ldx, N, W, Npad, Npad * Npad, alpha, Npad, tpart);
+            KL(c);
+        } else {
+            CU(cudaMemsetAsync(tpart, 0, sizeof(double) * (size_t)nb * T * T * 2, st));
+        }
+        nlml_finish_kernel<<<nb, 256, 0, st>>>(Kb, Npad, Npad * Npad, N, beta, Npad, tpart, T * T, dinfo, out);
+        KL(c);
+        CU(cudaMemcpyAsync(hout.data(), out, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hinfo.data(), dinfo, sizeof(int) * nb, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (int b = 0; b < nb; ++b) {
+            nlml[r0 + b] = hout[3 * b];
+            if (grad) { grad[2 * (r0 + b)] = hout[3 * b + 1]; grad[2 * (r0 + b) + 1] = hout[3 * b + 2]; }
+            if (info) info[r0 + b] = hinfo[b];
+        }
+    }
+    if (3 * mat * Rc > ((size_t)2 << 30)) {        // do not sit on multi-GB scratch between calls
+        ws_release(c, WS_NLML_K); ws_release(c, WS_NLML_LINV); ws_release(c, WS_NLML_W);
+    }
+    return ABO_OK;
+}

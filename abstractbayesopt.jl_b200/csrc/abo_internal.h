@@ -1,6 +1,7 @@
 // abo_internal.h — private structures shared by the translation units of libabo_cuda.so
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <utility>
 #include <vector>
 #include <cuda_runtime.h>
@@ -67,6 +68,16 @@ struct abo_gp {
     std::vector<double> hX, hY;           // host copies of the conditioning data (ABI layout)
 };
 
+// Julia `isless` order on Float64 as an unsigned key: NaN largest, -0.0 < 0.0
+static inline uint64_t ordkey(double v) {
+    if (v != v) return ~0ull;
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+int gp_alloc(abo_gp* g, int64_t Npad, int64_t ldx);
+void ws_release(abo_ctx* c, int slot);
 int ws_get(abo_ctx* c, int slot, size_t bytes, void** out);
 int pinned_get(abo_ctx* c, size_t bytes, void** out);
 int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strideA, double* Dinv, int64_t strideD,

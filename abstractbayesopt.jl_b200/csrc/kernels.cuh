@@ -551,4 +551,200 @@ __global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
     if (t < n) p[t] = v;
 }
 
+// ------------------------------------------------------------------------------------------
+// O(n^2) row append (StandardGP, p = 1): kernels around the two TRMVs
+// ------------------------------------------------------------------------------------------
+// kv[i] = sig2 * phi(|| xs_i - s*x_new ||^2), zero in the padding
+__global__ void kvec_kernel(KSpec spec, const double* __restrict__ XsT, int64_t ldx, int64_t n, int64_t Npad,
+                            const double* __restrict__ xnew, double* __restrict__ kv) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= Npad) return;
+    if (i >= n) { kv[i] = 0.0; return; }
+    double u = 0.0;
+    for (int k = 0; k < spec.d; ++k) {
+        double df = XsT[k * ldx + i] - spec.s * xnew[k];
+        u = fma(df, df, u);
+    }
+    double p, dp, ddp;
+    phi_eval(spec.kind, u, p, dp, ddp);
+    kv[i] = spec.scale * p;
+}
+// out[0] = sum v[i]^2 (single block, fixed-order tree)
+__global__ void __launch_bounds__(1024) sumsq_vec_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) s = fma(v[i], v[i], s);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+// commit the new row n:  L[n][:n] = w, L[n][n] = l ; Linv[n][:n] = -r/l, Linv[n][n] = 1/l ;
+// delta[n], beta[n] = Linv[n][:n].delta + delta_n/l ; alpha[:n] += Linv[n][:n]*beta_n ; alpha[n] = beta_n/l ;
+// XsT[:, n] = s*x_new.      Single block.
+__global__ void __launch_bounds__(1024) append_commit_kernel(double* __restrict__ L, double* __restrict__ Linv, int64_t ld,
+                                                             int64_t n, const double* __restrict__ w,
+                                                             const double* __restrict__ r, double l, double delta_n,
+                                                             double* __restrict__ delta, double* __restrict__ beta,
+                                                             double* __restrict__ alpha, double* __restrict__ XsT,
+                                                             int64_t ldx, const double* __restrict__ xnew, int d, double s) {
+    __shared__ double sh[1024];
+    __shared__ double s_beta;
+    const double linv = 1.0 / l;
+    double acc = 0.0;
+    for (int64_t j = threadIdx.x; j < n; j += 1024) {
+        const double li = -r[j] * linv;
+        L[n * ld + j] = w[j];
+        Linv[n * ld + j] = li;
+        acc = fma(li, delta[j], acc);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double bn = sh[0] + delta_n * linv;
+        s_beta = bn;
+        L[n * ld + n] = l;
+        Linv[n * ld + n] = linv;
+        delta[n] = delta_n;
+        beta[n] = bn;
+        alpha[n] = bn * linv;
+    }
+    __syncthreads();
+    const double bn = s_beta;
+    for (int64_t j = threadIdx.x; j < n; j += 1024) alpha[j] = fma(Linv[n * ld + j], bn, alpha[j]);
+    for (int k = threadIdx.x; k < d; k += 1024) XsT[k * ldx + n] = s * xnew[k];
+}
+// grow a padded lower-triangular matrix: copy the old Npad x Npad block, identity in the new part
+__global__ void grow_matrix_kernel(const double* __restrict__ src, int64_t old_pad, int64_t old_ld,
+                                   double* __restrict__ dst, int64_t new_pad) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= new_pad * new_pad) return;
+    const int64_t r = t / new_pad, c = t % new_pad;
+    dst[t] = (r < old_pad && c < old_pad) ? src[r * old_ld + c] : (r == c ? 1.0 : 0.0);
+}
+
+// ------------------------------------------------------------------------------------------
+// batched NLML (value + analytic gradient)
+// ------------------------------------------------------------------------------------------
+// per-batch scaled coordinates: XsT[b][k*ldx + i] = s_b * X[i*d + k]
+__global__ void scale_transpose_batched_kernel(const double* __restrict__ X, double* __restrict__ XsT, int64_t n, int d,
+                                               int64_t ldx, const double* __restrict__ sb) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= ldx * d) return;
+    int k = (int)(t / ldx);
+    int64_t i = t % ldx;
+    XsT[(int64_t)blockIdx.y * ldx * d + t] = (i < n) ? sb[blockIdx.y] * X[i * d + k] : 0.0;
+}
+// d/dlog(l) of a gradKernel entry.  s = 1/l, u = s^2 r^2, D = s * Delta:
+//   ds = -s, du = -2u, dD = -D.  uphi3 = u * (third derivative of phi at u).
+__device__ __forceinline__ double gk_dlogl_entry(const KSpec& ks, double u, double dp, double ddp, double uphi3, int a,
+                                                 int b, double Da, double Db) {
+    if (a == 0 && b == 0) return -2.0 * ks.scale * dp * u;
+    if (b == 0) return -4.0 * ks.scale * ks.s * Da * (dp + u * ddp);
+    if (a == 0) return 4.0 * ks.scale * ks.s * Db * (dp + u * ddp);
+    const double s2 = ks.s * ks.s;
+    return ks.scale * (16.0 * s2 * ddp * Da * Db + 8.0 * s2 * uphi3 * Da * Db + (a == b ? 4.0 * s2 * (dp + u * ddp) : 0.0));
+}
+__device__ __forceinline__ double u_phi3(int kind, double u) {
+    if (kind == K_SE) return -u * exp(-u / 2) / 8;
+    const double r = sqrt(u);
+    if (kind == K_M52 || kind == K_AM52 || kind == K_ADM52) {
+        if (kind == K_AM52 && u < 1e-10) return 0.0;
+        return -(25.0 * 2.23606797749978969641 / 24.0) * r * exp(-2.23606797749978969641 * r);
+    }
+    if (kind == K_AM72 && u < 1e-10) return 0.0;
+    return -(343.0 / 120.0) * u * exp(-2.64575131106459059050 * r);
+}
+// per lower tile:  part[b][tile][0] = sum_ij M_ij dK_ij/dlog l ,  part[..][1] = sum_ij M_ij K_ij
+// with M = Cinv - alpha alpha^T, counted over the FULL symmetric matrix (strict-lower entries x2).
+// grid (T, T, batch), 256 threads, tiles above the diagonal write zeros.
+__global__ void __launch_bounds__(256) nlml_grad_tile_kernel(KSpec spec, KmatBatch bt, const double* __restrict__ XsT,
+                                                             int64_t ldx, int64_t N, const double* __restrict__ Cinv,
+                                                             int64_t ld, int64_t strideC, const double* __restrict__ alpha,
+                                                             int64_t strideV, double* __restrict__ part) {
+    __shared__ double sh[2][256];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    const int T = gridDim.x;
+    double g0 = 0.0, g1 = 0.0;
+    if (bj <= bi) {
+        spec.s = bt.s[blockIdx.z]; spec.scale = bt.scale[blockIdx.z];
+        const double* X = XsT + (int64_t)blockIdx.z * bt.strideX;
+        const double* Cb = Cinv + (int64_t)blockIdx.z * strideC;
+        const double* al = alpha + (int64_t)blockIdx.z * strideV;
+        const int c = threadIdx.x & 127;
+        const int64_t gc = (int64_t)bj * NB + c;
+        const int64_t j = gc / spec.p;
+        const int b = (int)(gc % spec.p);
+        for (int r = threadIdx.x >> 7; r < NB; r += 2) {
+            const int64_t gr = (int64_t)bi * NB + r;
+            if (gr >= N || gc >= N || gc > gr) continue;
+            const int64_t i = gr / spec.p;
+            const int a = (int)(gr % spec.p);
+            double u = 0.0, Da = 0.0, Db = 0.0;
+            for (int k = 0; k < spec.d; ++k) {
+                double df = X[k * ldx + i] - X[k * ldx + j];
+                u = fma(df, df, u);
+                if (k == a - 1) Da = df;
+                if (k == b - 1) Db = df;
+            }
+            double p, dp, ddp;
+            phi_eval(spec.kind, u, p, dp, ddp);
+            const double kv = gk_entry(spec, p, dp, ddp, a, b, Da, Db);
+            const double dk = gk_dlogl_entry(spec, u, dp, ddp, u_phi3(spec.kind, u), a, b, Da, Db);
+            const double m = (Cb[gr * ld + gc] - al[gr] * al[gc]) * (gr == gc ? 1.0 : 2.0);
+            g0 = fma(m, dk, g0);
+            g1 = fma(m, kv, g1);
+        }
+    }
+    sh[0][threadIdx.x] = g0; sh[1][threadIdx.x] = g1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double* o = part + ((int64_t)blockIdx.z * T * T + (int64_t)bi * T + bj) * 2;
+        o[0] = sh[0][0]; o[1] = sh[1][0];
+    }
+}
+// one block per batch: nlml = (N log 2pi + 2 sum log L_ii + ||beta||^2) / 2, grad = (sum of tile partials) / 2
+__global__ void __launch_bounds__(256) nlml_finish_kernel(const double* __restrict__ L, int64_t ld, int64_t strideM, int64_t N,
+                                                          const double* __restrict__ beta, int64_t strideV,
+                                                          const double* __restrict__ part, int ntile,
+                                                          const int* __restrict__ info, double* __restrict__ out) {
+    __shared__ double sh[4][256];
+    const double* Lb = L + (int64_t)blockIdx.x * strideM;
+    const double* bb = beta + (int64_t)blockIdx.x * strideV;
+    double ld_ = 0.0, qq = 0.0, g0 = 0.0, g1 = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += 256) { ld_ += log(Lb[i * ld + i]); qq = fma(bb[i], bb[i], qq); }
+    for (int t = threadIdx.x; t < ntile; t += 256) {
+        g0 += part[((int64_t)blockIdx.x * ntile + t) * 2];
+        g1 += part[((int64_t)blockIdx.x * ntile + t) * 2 + 1];
+    }
+    sh[0][threadIdx.x] = ld_; sh[1][threadIdx.x] = qq; sh[2][threadIdx.x] = g0; sh[3][threadIdx.x] = g1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o)
+            for (int q = 0; q < 4; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double* o = out + (int64_t)blockIdx.x * 3;
+        if (info[blockIdx.x] != 0) {
+            o[0] = CUDART_INF; o[1] = CUDART_NAN; o[2] = CUDART_NAN;
+        } else {
+            o[0] = 0.5 * ((double)N * 1.8378770664093454836 + 2.0 * sh[0][0] + sh[1][0]);
+            o[1] = 0.5 * sh[2][0];
+            o[2] = 0.5 * sh[3][0];
+        }
+    }
+}
+
 }  // namespace abo

@@ -216,3 +216,103 @@ def test_standardgp_copy_semantics(abo):
     cp = abo.copy(gp)
     assert cp.kernel is gp.kernel and cp.gpx is not gp.gpx
     assert abo.posterior_mean(cp, [0.25])[0] == abo.posterior_mean(gp, [0.25])[0]
+
+
+# ---- O(n^2) row append vs a full re-fit (the reference re-fits: bayesian_opt.jl:125) --------
+def test_append_matches_refit(abo, orc):
+    c = orc.make_config("C2", n=330, m=500)
+    kern = make_kernel(abo, 1, c["inv_ls"], 1.0)
+    gp = abo.update(abo.StandardGP(kern, c["noise"]), c["X"][:190], c["y"][:190])
+    for i in range(190, 330):                       # crosses two padding tiles (256, 384 -> grows)
+        gp = abo.update(gp, c["X"][:i + 1], c["y"][:i + 1])
+    assert gp.gpx.n() == 330
+    post = orc.fit_standard(c["X"], c["y"], 1, c["inv_ls"], 1.0, c["noise"])
+    mu_o, var_o = orc.posterior_mean_var(post, c["Xc"])
+    assert close(abo.posterior_mean(gp, c["Xc"]), mu_o, 1.0)
+    assert close(abo.posterior_var(gp, c["Xc"]), var_o, 1.0)
+    assert np.max(np.abs(gp.gpx.factor(0) - post.U.T)) < 1e-10
+    full = abo.update(abo.StandardGP(kern, c["noise"]), c["X"], c["y"])
+    assert close(abo.posterior_var(gp, c["Xc"]), abo.posterior_var(full, c["Xc"]), 1.0, 1e-11)
+
+
+def test_append_is_transactional(abo, orc):
+    gp = abo.update(abo.StandardGP(abo.SqExponentialKernel(), 0.0), [[-1.0, -1.0], [5.0, -5.0]], [2.0, 50.0])
+    h = gp.gpx.clone()
+    with pytest.raises(abo.PosDefException) as ei:
+        h.append([-1.0 + 1e-12, -1.0 + 1e-12], [2.0])
+    assert ei.value.info == 3 and h.n() == 2
+    m1, v1 = h.posterior(np.array([[0.3, 0.2]]))
+    m0, v0 = gp.gpx.posterior(np.array([[0.3, 0.2]]))
+    assert m1[0] == m0[0] and v1[0] == v0[0]
+
+
+# ---- batched NLML + analytic gradient (StandardGP.jl:99-114, bayesian_opt.jl:259-300) ------
+def test_nlml_known_answer(abo):
+    gp = abo.StandardGP(abo.SqExponentialKernel(), 0.1)
+    val = abo.nlml(gp, [math.log(1.0), math.log(1.0)], [0.0, 0.5, 1.0], [0.0, 0.25, 1.0])   # test_surrogates.jl:145-170
+    assert abs(val - 2.6769327097262567) < 1e-10
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_nlml_batch_standard(abo, orc, kind):
+    rng = np.random.default_rng(11 + kind)
+    n, d = 300, 4
+    X = rng.random((n, d)); y = np.sin(3 * X).sum(1) + 0.05 * rng.standard_normal(n)
+    theta = np.column_stack([np.log(rng.uniform(0.2, 2.0, 7)), np.log(rng.uniform(0.3, 5.0, 7))])
+    gp = abo.StandardGP(make_kernel(abo, kind, 1.0, 1.0), 1e-3, mean=0.1)
+    val, grad, info = abo.nlml_batch(gp, theta, X, y)
+    assert np.all(info == 0)
+    for r in range(theta.shape[0]):
+        v_o, g_o = orc.nlml(X, y, kind, theta[r, 0], theta[r, 1], 1e-3, mean_c=0.1, want_grad=True)
+        assert abs(val[r] - v_o) <= 1e-9 * abs(v_o), (val[r], v_o)
+        assert np.all(np.abs(grad[r] - g_o) <= 1e-7 * np.maximum(np.abs(g_o), 1.0)), (grad[r], g_o)
+
+
+def test_nlml_batch_gradient_gp(abo, orc):
+    rng = np.random.default_rng(5)
+    n, d = 25, 3
+    X = -2 + 4 * rng.random((n, d)); Y = orc.rosenbrock_with_grad(X) / 100.0
+    theta = np.array([[math.log(1.2), math.log(2.0)], [math.log(0.8), math.log(0.7)], [math.log(2.5), math.log(4.0)]])
+    for kind in (0, 3, 5, 6):
+        gp = abo.GradientGP(make_kernel(abo, kind, 1.0, 1.0), d + 1, 1e-4)
+        val, grad, info = abo.nlml_batch(gp, theta, X, Y)
+        assert np.all(info == 0)
+        for r in range(3):
+            v_o, g_o = orc.nlml(X, orc.prep_output(Y), kind, theta[r, 0], theta[r, 1], 1e-4, gradient_gp=True, want_grad=True)
+            assert abs(val[r] - v_o) <= 1e-9 * abs(v_o)
+            assert np.all(np.abs(grad[r] - g_o) <= 2e-6 * np.maximum(np.abs(g_o), 1.0)), (kind, grad[r], g_o)
+
+
+def test_nlml_batch_reports_failed_restarts(abo):
+    X = np.array([[0.0, 0.0], [1.0, 1.0], [1.0, 1.0], [2.0, 0.5]]); y = np.array([0.0, 1.0, 1.0, 0.5])
+    gp = abo.StandardGP(abo.SqExponentialKernel(), 0.0)                 # duplicate point, no noise
+    val, grad, info = abo.nlml_batch(gp, np.array([[0.0, 0.0], [0.5, 0.2]]), X, y)
+    assert np.all(info == 3) and np.all(np.isinf(val))
+
+
+def test_hyperparameter_optimisation_improves_nlml(abo, orc):
+    # test/test_bayesian_opt.jl:108-137, 597-653: returns a model, NLML does not get worse
+    rng = np.random.default_rng(0)
+    X = rng.random((60, 2)) * 4 - 2; y = np.sum(X ** 2, axis=1)
+    y = (y - y.mean()) / y.std(ddof=1)
+    gp = abo.StandardGP(1.0 * abo.with_lengthscale(abo.SqExponentialKernel(), 0.3), 1e-6)
+    old = [math.log(0.3), math.log(1.0)]
+    new = abo.optimize_hyperparameters(gp, X, y, old, num_restarts=3, rng=rng)
+    assert isinstance(new, abo.StandardGP)
+    th = [math.log(abo.get_lengthscale(new)[0]), math.log(abo.get_scale(new)[0])]
+    assert abo.nlml(new, th, X, y) <= abo.nlml(gp, old, X, y) + 1e-6
+
+
+def test_bo_loop_branin(abo, orc):
+    # config C1 shape at reduced size: StandardGP-SE + EI on 2-D Branin
+    rng = np.random.default_rng(42)
+    dom = abo.ContinuousDomain([-5.0, 0.0], [10.0, 15.0])
+    f = lambda x: float(orc.branin(np.asarray(x)[None, :])[0])
+    X0 = dom.lower + (dom.upper - dom.lower) * rng.random((10, 2))
+    y0 = [f(x) for x in X0]
+    gp = abo.StandardGP(1.0 * abo.with_lengthscale(abo.SqExponentialKernel(), 3.0), 1e-6)
+    bo = abo.BOStruct(f, abo.ExpectedImprovement(0.01, min(y0)), gp, dom, list(X0), y0, 8, 0.0)
+    bo, acq_list, _ = abo.optimize(bo, standardize="mean_scale", hyper_params=None, n_grid=4000, n_local=4, rng=rng)
+    assert len(bo.xs) == 10 + 9 and len(acq_list) == 9          # max_iter + 1 passes (bayesian_opt.jl:163-165)
+    assert min(float(v) for v in bo.ys_non_std) <= min(y0) + 1e-12
+    assert all(a >= 0 for a in acq_list)
