@@ -284,10 +284,14 @@ def test_nlml_batch_gradient_gp(abo, orc):
 
 
 def test_nlml_batch_reports_failed_restarts(abo):
-    X = np.array([[0.0, 0.0], [1.0, 1.0], [1.0, 1.0], [2.0, 0.5]]); y = np.array([0.0, 1.0, 1.0, 0.5])
-    gp = abo.StandardGP(abo.SqExponentialKernel(), 0.0)                 # duplicate point, no noise
-    val, grad, info = abo.nlml_batch(gp, np.array([[0.0, 0.0], [0.5, 0.2]]), X, y)
+    # the reference's own ill-conditioned set-up (test/test_bayesian_opt.jl:749-786): noise 0 and a
+    # point 1e-12 away from an existing one -> pivot 3 is exactly <= 0 whatever the rounding
+    X = np.array([[-1.0, -1.0], [5.0, -5.0], [-1.0 + 1e-12, -1.0 + 1e-12]]); y = np.array([2.0, 50.0, 2.0])
+    gp = abo.StandardGP(abo.SqExponentialKernel(), 0.0)
+    val, grad, info = abo.nlml_batch(gp, np.array([[0.0, 0.0], [0.5, 0.0]]), X, y)   # sigma^2 = 1: l31 = 1 exactly
     assert np.all(info == 3) and np.all(np.isinf(val))
+    val2, _, info2 = abo.nlml_batch(gp, np.array([[0.0, 0.0]]), X[:2], y[:2])      # the first two points are fine
+    assert info2[0] == 0 and np.isfinite(val2[0])
 
 
 def test_hyperparameter_optimisation_improves_nlml(abo, orc):
