@@ -152,6 +152,15 @@ class Context:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         check(lib().abo_ctx_init_rank(self._h, rank, nranks, buf))
 
+    def topk_allgather(self, k, idx, val):
+        """NCCL all-gather + merge of per-rank (global index, value) top-k lists."""
+        ti = np.zeros(k, dtype=np.int64); tv = np.zeros(k)
+        cnt = min(len(idx), k)
+        ti[:cnt] = idx[:cnt]; tv[:cnt] = val[:cnt]
+        out = C.c_int64(0)
+        check(lib().abo_topk_allgather(self._h, k, cnt, ptr(ti), ptr(tv), C.byref(out)))
+        return ti[:out.value], tv[:out.value]
+
     def close(self):
         if self._h is not None and self._h.value:
             lib().abo_ctx_destroy(self._h)

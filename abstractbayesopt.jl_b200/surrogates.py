@@ -157,6 +157,16 @@ def update_surrogate(model, xs, ys, allow_append=True):
     return new
 
 
+def empty_posterior_like(model, d):
+    """A copy of `model` holding an un-fitted device handle of the right (kernel, d, p): the receive
+    side of `sync_posterior` on non-root ranks."""
+    new = model.copy()
+    new.ctx = model.ctx or default_context()
+    new.gpx = GpHandle(new.ctx, model.kernel.kernel_id, int(d), model.p)
+    new.gpx.set_params(model.kernel.inv_lengthscale, model.kernel.scale, model.noise_var, np.atleast_1d(model.mean_c))
+    return new
+
+
 def _need_posterior(model):
     if model.gpx is None:
         raise _lib.AboCudaError("surrogate has no posterior: call update(model, xs, ys) first")

@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--m", type=int, default=M_PER_GPU, help="candidates per GPU per step")
+    ap.add_argument("--cands", dest="m", type=int, default=M_PER_GPU, help="candidates per GPU per step")
     ap.add_argument("--n", type=int, default=N_OBS)
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -289,7 +289,7 @@ def main():
     trmm_ms, trmm_n = prof_ms[1], max(prof_n[1], 1)
     cand_per_launch = m * args.steps / trmm_n
     achieved = (float(n) * n * cand_per_launch) / (trmm_ms / trmm_n * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<KC,KC,SUMSQ> (W = L^-1 K*, column sum of squares)",
+    roofline = {"bound": "tensor", "kernel": "sweep_tma_kernel (TMA + mbarrier + DMMA: W = L^-1 K*, fused column sum of squares)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_flop_per_candidate": float(n) * n,
                 "candidates_per_launch": cand_per_launch, "avg_launch_ms": trmm_ms / trmm_n,

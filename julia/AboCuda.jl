@@ -1,0 +1,154 @@
+# AboCuda.jl — the Julia side of the drop-in: new AbstractSurrogate / AbstractAcquisition methods
+# that `ccall` into libabo_cuda.so (include/abo.h).  Written against the header; Julia is not
+# available in the build image, so this file is reviewed, not executed (see INTEGRATION.md).
+#
+# Usage inside AbstractBayesOpt.jl (src/AbstractBayesOpt.jl:16-66): `include("AboCuda.jl")` after
+# the surrogates are defined; `BOStruct` / `optimize` (src/bayesian_opt.jl:364-449) run unchanged.
+module AboCuda
+
+using LinearAlgebra
+using ..AbstractBayesOpt: AbstractSurrogate, AbstractAcquisition, ExpectedImprovement,
+    ProbabilityImprovement, UpperConfidenceBound, StandardGP, extract_scale_and_lengthscale
+import ..AbstractBayesOpt: update, posterior_mean, posterior_var, nlml, nlml_ls, prep_input, prep_output,
+    get_lengthscale, get_scale, get_kernel_constructor, _get_minimum, _update_model_parameters,
+    get_mean_std, std_y, rescale_model
+
+const LIB = get(ENV, "ABO_CUDA_LIB", "libabo_cuda.so")
+const ABO_OK, ABO_ERR_INVALID, ABO_ERR_DIM, ABO_ERR_NOT_POSDEF = 0, 1, 2, 3
+
+last_error() = unsafe_string(ccall((:abo_last_error, LIB), Cstring, ()))
+function check(rc::Int32, info::Integer=0)
+    rc == ABO_OK && return nothing
+    rc == ABO_ERR_NOT_POSDEF && throw(LinearAlgebra.PosDefException(info))   # caught at bayesian_opt.jl:126-141
+    rc == ABO_ERR_DIM && throw(DimensionMismatch(last_error()))              # test_bayesian_opt.jl:788-817
+    rc == ABO_ERR_INVALID && throw(ArgumentError(last_error()))
+    error("libabo_cuda status $rc: $(last_error())")
+end
+
+mutable struct Ctx
+    h::Ptr{Cvoid}
+    function Ctx(device::Integer=0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:abo_ctx_create, LIB), Int32, (Int32, Ref{Ptr{Cvoid}}), device, r))
+        c = new(r[]); finalizer(c -> ccall((:abo_ctx_destroy, LIB), Int32, (Ptr{Cvoid},), c.h), c); c
+    end
+end
+const DEFAULT_CTX = Ref{Union{Nothing,Ctx}}(nothing)
+ctx() = (DEFAULT_CTX[] === nothing && (DEFAULT_CTX[] = Ctx(0)); DEFAULT_CTX[])
+
+mutable struct Handle            # abo_gp*: a conditioned surrogate resident in HBM
+    h::Ptr{Cvoid}
+    Handle(h) = (x = new(h); finalizer(x -> ccall((:abo_gp_destroy, LIB), Int32, (Ptr{Cvoid},), x.h), x); x)
+end
+
+const KERNEL_IDS = Dict(:SqExponentialKernel => 0, :Matern52Kernel => 1, :Matern72Kernel => 2,
+    :ApproxMatern52Kernel => 3, :ApproxMatern72Kernel => 4, :ADMatern52Kernel => 5, :ADMatern72Kernel => 6)
+
+"""GPU twin of StandardGP (src/surrogates/StandardGP.jl:11-16): same prior description, the posterior
+is a device handle instead of an AbstractGPs.PosteriorGP."""
+struct CuStandardGP{T} <: AbstractSurrogate
+    prior::StandardGP{T}              # keeps kernel / noise / mean exactly as the reference stores them
+    gpx::Union{Nothing,Handle}
+end
+CuStandardGP(kernel, noise_var; mean=nothing) = CuStandardGP(StandardGP(kernel, noise_var; mean=mean), nothing)
+
+get_lengthscale(m::CuStandardGP) = get_lengthscale(m.prior)
+get_scale(m::CuStandardGP) = get_scale(m.prior)
+get_kernel_constructor(m::CuStandardGP) = get_kernel_constructor(m.prior)
+prep_input(m::CuStandardGP, xs) = xs
+prep_output(m::CuStandardGP, ys) = ys
+_get_minimum(m::CuStandardGP, ys) = minimum(ys)
+get_mean_std(m::CuStandardGP, ys, choice) = get_mean_std(m.prior, ys, choice)
+std_y(m::CuStandardGP, ys, μ, σ) = std_y(m.prior, ys, μ, σ)
+rescale_model(m::CuStandardGP, σ) = CuStandardGP(rescale_model(m.prior, σ), nothing)
+_update_model_parameters(m::CuStandardGP, k) = CuStandardGP(_update_model_parameters(m.prior, k), nothing)
+
+kernel_id(m::CuStandardGP) = KERNEL_IDS[nameof(typeof(get_kernel_constructor(m)))]
+inv_lengthscale(m::CuStandardGP) = m.prior.gp.kernel.kernel.transform.s[1]   # the stored s, not 1/ℓ (SURVEY H4)
+mean_const(m::CuStandardGP) = m.prior.gp.mean isa AbstractGPs.ZeroMean ? 0.0 : m.prior.gp.mean.c
+
+function Base.copy(m::CuStandardGP)                                           # StandardGP.jl:26
+    m.gpx === nothing && return CuStandardGP(m.prior, nothing)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:abo_gp_clone, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), m.gpx.h, r))
+    CuStandardGP(m.prior, Handle(r[]))
+end
+
+points(xs::Vector{<:AbstractVector}) = reduce(hcat, xs)                       # d x n column-major = point-major
+points(xs::Vector{<:Real}) = reshape(collect(Float64, xs), 1, :)
+
+function update(m::CuStandardGP, xs::Vector, ys::Vector)                      # StandardGP.jl:79-83
+    X = Matrix{Float64}(points(xs)); d, n = size(X)
+    length(ys) == n || throw(DimensionMismatch("xs and ys have different lengths"))
+    y = collect(Float64, ys)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:abo_gp_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}),
+        ctx().h, kernel_id(m), d, 1, r))
+    h = Handle(r[])
+    mc = [Float64(mean_const(m))]
+    check(ccall((:abo_gp_set_params, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, Ptr{Float64}),
+        h.h, inv_lengthscale(m), get_scale(m)[1], m.prior.noise_var, mc))
+    info = Ref{Int64}(0)
+    rc = GC.@preserve X y ccall((:abo_gp_fit, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ref{Int64}),
+        h.h, X, y, n, info)
+    check(rc, info[])
+    CuStandardGP(m.prior, h)
+end
+
+function posterior(m::CuStandardGP, x::AbstractVector, want_mean::Bool, want_var::Bool)
+    Xc = Matrix{Float64}(points(collect(x))); mcount = size(Xc, 2)
+    μ = want_mean ? Vector{Float64}(undef, mcount) : Float64[]
+    v = want_var ? Vector{Float64}(undef, mcount) : Float64[]
+    check(GC.@preserve Xc μ v ccall((:abo_gp_posterior, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Float64}, Ptr{Float64}),
+        m.gpx.h, Xc, mcount, 1, want_mean ? pointer(μ) : C_NULL, want_var ? pointer(v) : C_NULL))
+    μ, v
+end
+posterior_mean(m::CuStandardGP, x::AbstractVector) = posterior(m, x, true, false)[1]   # StandardGP.jl:361-363
+posterior_var(m::CuStandardGP, x::AbstractVector) = posterior(m, x, false, true)[2]    # StandardGP.jl:377-379
+posterior_mean(m::CuStandardGP, x::Real) = posterior_mean(m, [x])
+posterior_var(m::CuStandardGP, x::Real) = posterior_var(m, [x])
+
+# ---- fused acquisitions: one sweep instead of two posterior passes (ExpectedImprovement.jl:40-45)
+acq_id(::ExpectedImprovement) = Int32(0); acq_params(a::ExpectedImprovement) = Float64[a.ξ, a.best_y]
+acq_id(::ProbabilityImprovement) = Int32(1); acq_params(a::ProbabilityImprovement) = Float64[a.ξ, a.best_y]
+acq_id(::UpperConfidenceBound) = Int32(2); acq_params(a::UpperConfidenceBound) = Float64[a.β]
+
+function acq_eval(a::AbstractAcquisition, m::CuStandardGP, x::AbstractVector; k::Integer=0)
+    Xc = Matrix{Float64}(points(collect(x))); mcount = size(Xc, 2)
+    scores = Vector{Float64}(undef, mcount); p = acq_params(a)
+    ti = Vector{Int64}(undef, max(k, 1)); tv = Vector{Float64}(undef, max(k, 1))
+    check(GC.@preserve Xc scores p ti tv ccall((:abo_acq_eval, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Float64}),
+        m.gpx.h, acq_id(a), p, Xc, mcount, scores, min(k, mcount), ti, tv))
+    scores, ti[1:min(k, mcount)] .+ 1, tv[1:min(k, mcount)]        # 0-based -> Julia indices
+end
+(a::ExpectedImprovement)(m::CuStandardGP, x::AbstractVector) = acq_eval(a, m, x)[1]
+(a::ProbabilityImprovement)(m::CuStandardGP, x::AbstractVector) = acq_eval(a, m, x)[1]
+(a::UpperConfidenceBound)(m::CuStandardGP, x::AbstractVector) = acq_eval(a, m, x)[1]
+
+# ---- nlml with ForwardDiff.Dual parameters (bayesian_opt.jl:284): value + analytic gradient from the
+#      device, re-assembled into a Dual (SURVEY H7)
+function nlml_value_grad(m::CuStandardGP, θ::Vector{Float64}, xs, ys)
+    X = Matrix{Float64}(points(xs)); d, n = size(X); y = collect(Float64, ys)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:abo_gp_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}), ctx().h, kernel_id(m), d, 1, r))
+    h = Handle(r[]); mc = [Float64(mean_const(m))]
+    check(ccall((:abo_gp_set_params, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, Ptr{Float64}),
+        h.h, inv_lengthscale(m), get_scale(m)[1], m.prior.noise_var, mc))
+    val = Ref{Float64}(0.0); g = zeros(2); info = Ref{Int32}(0)
+    check(GC.@preserve X y θ g ccall((:abo_nlml_batch, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ref{Float64}, Ptr{Float64}, Ref{Int32}),
+        h.h, X, y, n, θ, 1, val, g, info))
+    info[] != 0 && throw(LinearAlgebra.PosDefException(info[]))
+    val[], g
+end
+nlml(m::CuStandardGP, p::AbstractVector{<:AbstractFloat}, xs, ys) = nlml_value_grad(m, collect(Float64, p), xs, ys)[1]
+function nlml(m::CuStandardGP, p::AbstractVector{D}, xs, ys) where {T,V,N,D<:ForwardDiff.Dual{T,V,N}}
+    v, g = nlml_value_grad(m, Float64.(ForwardDiff.value.(p)), xs, ys)
+    parts = g[1] * ForwardDiff.partials(p[1]) + g[2] * ForwardDiff.partials(p[2])
+    ForwardDiff.Dual{T}(v, parts)
+end
+nlml_ls(m::CuStandardGP, log_ℓ, log_scale::Float64, xs, ys) = nlml(m, [log_ℓ, oftype(log_ℓ, log_scale)], xs, ys)
+
+end # module
