@@ -16,7 +16,7 @@ ABO_OK, ABO_ERR_INVALID, ABO_ERR_DIM, ABO_ERR_NOT_POSDEF, ABO_ERR_CUDA, ABO_ERR_
 # every symbol include/abo.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "abo_version", "abo_last_error", "abo_ctx_create", "abo_ctx_destroy", "abo_ctx_device", "abo_ctx_stream",
-    "abo_ctx_launch_count", "abo_ctx_profile", "abo_ctx_profile_read", "abo_gp_create", "abo_gp_destroy", "abo_gp_set_params", "abo_gp_fit", "abo_gp_append",
+    "abo_ctx_launch_count", "abo_ctx_profile", "abo_ctx_profile_read", "abo_debug_potf2_clocks", "abo_gp_create", "abo_gp_destroy", "abo_gp_set_params", "abo_gp_fit", "abo_gp_append",
     "abo_gp_clone", "abo_gp_n", "abo_gp_alpha", "abo_gp_factor", "abo_gp_posterior", "abo_acq_eval", "abo_acq_eval_dev",
     "abo_nlml_batch", "abo_potrf_dev", "abo_nccl_unique_id", "abo_ctx_init_rank", "abo_gp_sync",
     "abo_topk_allgather",
@@ -63,6 +63,7 @@ def lib():
             "abo_ctx_launch_count": [vp, C.POINTER(i64)],
             "abo_ctx_profile": [vp, i32],
             "abo_ctx_profile_read": [vp, vp, vp],
+            "abo_debug_potf2_clocks": [vp, vp],
             "abo_gp_create": [vp, i32, i32, i32, C.POINTER(vp)],
             "abo_gp_destroy": [vp],
             "abo_gp_set_params": [vp, dbl, dbl, dbl, vp],
@@ -141,6 +142,11 @@ class Context:
         ms = (C.c_double * 3)(); n = (C.c_int64 * 3)()
         check(lib().abo_ctx_profile_read(self._h, ms, n))
         return list(ms), list(n)
+
+    def potf2_clocks(self):
+        out = (C.c_int64 * 16)()
+        check(lib().abo_debug_potf2_clocks(self._h, out))
+        return list(out)
 
     def potrf_dev(self, dptr: int, n: int, ld: int) -> int:
         info = C.c_int64(0)

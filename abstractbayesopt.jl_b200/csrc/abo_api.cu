@@ -48,7 +48,8 @@ static int configure_kernels() {
     CU(configure_gemm<KC, MC, EPI_STORE>());
     CU(configure_gemm<MC, MC, EPI_STORE>());
     CU(configure_gemm<KC, KC, EPI_SUMSQ>());
-    CU(cudaFuncSetAttribute(gemm64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G64_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(gemm_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<64>::SMEM_BYTES));
+    CU(cudaFuncSetAttribute(gemm_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<32>::SMEM_BYTES));
     CU(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM_BYTES));
     CU(cudaFuncSetAttribute(sweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
     CU(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
@@ -189,6 +190,16 @@ int make_tmap_k4(CUtensorMap* map, const double* base, int64_t K, int64_t rows, 
     return ABO_OK;
 }
 
+extern "C" int32_t abo_debug_potf2_clocks(abo_ctx* c, int64_t out[16]) {
+    if (!c || !out) return abo_fail(ABO_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    long long h[16];
+    CU(cudaMemcpyFromSymbol(h, g_potf2_clk, sizeof h));
+    for (int i = 0; i < 16; ++i) out[i] = h[i];
+    return ABO_OK;
+}
+
 // grow-only workspace slots
 int ws_get(abo_ctx* c, int slot, size_t bytes, void** out) {
     auto& b = c->ws[slot];
@@ -231,7 +242,7 @@ int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strid
     for (int jb = 0; jb < T; ++jb) {
         double* Ajj = A + (int64_t)jb * NB * (ld + 1);
         double* Dj = Dinv + (int64_t)jb * NB * NB;
-        potf2_inv_kernel<<<batch, 512, POTF2_SMEM_BYTES, st>>>(Ajj, ld, strideA, Dj, strideD, info, jb * NB);
+        potf2_inv_kernel<<<batch, POTF2_THREADS, POTF2_SMEM_BYTES, st>>>(Ajj, ld, strideA, Dj, strideD, info, jb * NB);
         KL(c);
         const int rem = (int)(Npad - (int64_t)(jb + 1) * NB);
         if (rem <= 0) break;
@@ -265,9 +276,11 @@ int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strid
 // ------------------------------------------------------------------------------------------
 int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Dinv, int* info) {
     const int T = (int)(Npad / NB);
-    const int OB = 4;
+    static const int OB_env = getenv("ABO_POTRF_OB") ? atoi(getenv("ABO_POTRF_OB")) : 4;
+    static const bool one_stream = getenv("ABO_POTRF_1STREAM") != nullptr;
+    const int OB = std::max(1, OB_env);
     if (T <= OB) return potrf_blocked(c, A, Npad, ld, 0, Dinv, 0, info, 1);
-    cudaStream_t sp = c->stream, su = c->stream2;
+    cudaStream_t sp = c->stream, su = one_stream ? c->stream : c->stream2;
     CUtensorMap tmL;
     int rc = make_tmap_k4(&tmL, A, Npad, Npad, ld);
     if (rc) return rc;
@@ -280,7 +293,7 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
         for (int jp = Jb; jp < je; ++jp) {
             double* Ajj = A + (int64_t)jp * NB * (ld + 1);
             double* Dj = Dinv + (int64_t)jp * NB * NB;
-            potf2_inv_kernel<<<1, 512, POTF2_SMEM_BYTES, sp>>>(Ajj, ld, 0, Dj, 0, info, jp * NB);
+            potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM_BYTES, sp>>>(Ajj, ld, 0, Dj, 0, info, jp * NB);
             KL(c);
             const int rem = (T - jp - 1) * NB;
             if (rem <= 0) break;
@@ -288,7 +301,7 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
             GemmParams g{};
             g.A = P; g.lda = ld; g.B = Dj; g.ldb = NB; g.C = P; g.ldc = ld;
             g.M = rem; g.N = NB; g.K = NB; g.alpha = 1.0; g.beta = 0.0; g.flags = 0;
-            CU(launch_gemm64(g, 1, sp));
+            CU(launch_gemm_small<32>(g, 1, sp));
             KL(c);
             const int ncol = (je - jp - 1) * NB;       // remaining columns of this outer block
             if (ncol > 0) {
@@ -296,7 +309,7 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
                 s.A = P; s.lda = ld; s.B = P; s.ldb = ld;
                 s.C = Ajj + (int64_t)NB * (ld + 1); s.ldc = ld;
                 s.M = rem; s.N = ncol; s.K = NB; s.alpha = -1.0; s.beta = 1.0; s.flags = LOWER_ONLY;
-                CU(launch_gemm64(s, 1, sp));
+                CU(launch_gemm_small<32>(s, 1, sp));
                 KL(c);
             }
         }

@@ -196,43 +196,50 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmParams p
 }
 
 // ------------------------------------------------------------------------------------------
-// 64 x 128 tile variant (K-contiguous operands, store epilogue) for the latency-critical panel
-// operations of the Cholesky (TRSM-as-GEMM and the in-block SYRK, K = 128): twice as many CTAs,
-// half the time per tile.  8 warps as 2 (M) x 4 (N), warp tile 32 x 32.
+// BMT x 128 tile variants (BMT = 64 or 32; K-contiguous operands, store epilogue) for the
+// latency-critical panel operations of the Cholesky (TRSM-as-GEMM and the in-block SYRK,
+// K = 128): 2x / 4x as many CTAs, half / quarter of the time per tile.
+// 8 warps as (BMT/32) along M x (256/BMT) along N, warp tile 32 x (BMT/2).
 // ------------------------------------------------------------------------------------------
-constexpr int G64_A_DOUBLES = 4 * 64 * 4, G64_B_DOUBLES = 4 * 128 * 4;
-constexpr int G64_SMEM_BYTES = STAGES * (G64_A_DOUBLES + G64_B_DOUBLES) * (int)sizeof(double);
+template <int BMT>
+struct GemmS {
+    static constexpr int WM = BMT / 32, WN = 8 / WM, WNC = 128 / WN, NT = WNC / 8;
+    static constexpr int A_DOUBLES = 4 * BMT * 4, B_DOUBLES = 4 * 128 * 4;
+    static constexpr int SMEM_BYTES = STAGES * (A_DOUBLES + B_DOUBLES) * (int)sizeof(double);
+};
 
-__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm64_kernel(GemmParams p) {
+template <int BMT>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_small_kernel(GemmParams p) {
+    using S = GemmS<BMT>;
     extern __shared__ __align__(16) double smem[];
     double* sA = smem;
-    double* sB = smem + STAGES * G64_A_DOUBLES;
+    double* sB = smem + STAGES * S::A_DOUBLES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * BN;
+    const int wm = (warp % S::WM) * 32, wn = (warp / S::WM) * S::WNC;
+    const int m0 = blockIdx.y * BMT, n0 = blockIdx.x * BN;
     if ((p.flags & LOWER_ONLY) && n0 > m0) return;
     const double* A = p.A + (int64_t)blockIdx.z * p.strideA;
     const double* B = p.B + (int64_t)blockIdx.z * p.strideB;
     const int nk = p.K / BK;
 
-    double acc[4][4][2];
+    double acc[4][S::NT][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int j = 0; j < S::NT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
     auto load_stage = [&](int s, int kt) {
         const int k0 = kt * BK;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {                     // A: 64 rows x 8 chunks
+        for (int q = 0; q < BMT / 32; ++q) {              // A: BMT rows x 8 chunks of 16 B
             int c = tid + GEMM_THREADS * q, row = c >> 3, ch = c & 7;
-            cp_async16(sA + s * G64_A_DOUBLES + (((ch >> 1) * 64 + row) << 2) + ((ch & 1) << 1),
+            cp_async16(sA + s * S::A_DOUBLES + (((ch >> 1) * BMT + row) << 2) + ((ch & 1) << 1),
                        A + (int64_t)(m0 + row) * p.lda + k0 + 2 * ch);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {                     // B: 128 rows x 8 chunks
             int c = tid + GEMM_THREADS * q, row = c >> 3, ch = c & 7;
-            cp_async16(sB + s * G64_B_DOUBLES + (((ch >> 1) * 128 + row) << 2) + ((ch & 1) << 1),
+            cp_async16(sB + s * S::B_DOUBLES + (((ch >> 1) * 128 + row) << 2) + ((ch & 1) << 1),
                        B + (int64_t)(n0 + row) * p.ldb + k0 + 2 * ch);
         }
     };
@@ -249,22 +256,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm64_kernel(GemmParams p) {
             if (nxt < nk) load_stage(nxt % STAGES, nxt);
             cp_async_commit();
         }
-        const double* a_s = sA + (kt % STAGES) * G64_A_DOUBLES;
-        const double* b_s = sB + (kt % STAGES) * G64_B_DOUBLES;
+        const double* a_s = sA + (kt % STAGES) * S::A_DOUBLES;
+        const double* b_s = sB + (kt % STAGES) * S::B_DOUBLES;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-            double a[4], b[4];
+            double a[4], b[S::NT];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                // rows wm + i*8 .. : only 32 rows per warp -> i < 4 covers 32 rows
-                a[i] = a_s[((kk * 64 + wm + i * 8 + (lane >> 2)) << 2) + (lane & 3)];
-            }
+            for (int i = 0; i < 4; ++i) a[i] = a_s[((kk * BMT + wm + i * 8 + (lane >> 2)) << 2) + (lane & 3)];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = b_s[((kk * 128 + wn + j * 8 + (lane >> 2)) << 2) + (lane & 3)];
+            for (int j = 0; j < S::NT; ++j) b[j] = b_s[((kk * 128 + wn + j * 8 + (lane >> 2)) << 2) + (lane & 3)];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < S::NT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
     cp_async_wait<0>();
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm64_kernel(GemmParams p) {
     for (int i = 0; i < 4; ++i) {
         int row = m0 + wm + i * 8 + (lane >> 2);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < S::NT; ++j) {
             int col = n0 + wn + j * 8 + 2 * (lane & 3);
             double2* dst = reinterpret_cast<double2*>(C + (int64_t)row * p.ldc + col);
             double2 v;
@@ -289,10 +293,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm64_kernel(GemmParams p) {
     }
 }
 
-inline cudaError_t launch_gemm64(const GemmParams& p, int batch, cudaStream_t st) {
+template <int BMT>
+inline cudaError_t launch_gemm_small(const GemmParams& p, int batch, cudaStream_t st) {
     if (p.M <= 0 || p.N <= 0 || batch <= 0) return cudaSuccess;
-    dim3 grid(p.N / BN, p.M / 64, batch);
-    gemm64_kernel<<<grid, GEMM_THREADS, G64_SMEM_BYTES, st>>>(p);
+    dim3 grid(p.N / BN, p.M / BMT, batch);
+    gemm_small_kernel<BMT><<<grid, GEMM_THREADS, GemmS<BMT>::SMEM_BYTES, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -131,16 +131,19 @@ __global__ void __launch_bounds__(256) kmat_kernel(KSpec spec, const double* __r
 // 128 x 128 diagonal block:  A = L L^T in shared memory (right-looking), then L^-1 by
 // recursive doubling (8 -> 16 -> ... -> 128).  Writes L (upper part zeroed) back in place and
 // L^-1 to Dinv.  A non-positive pivot sets *info (1-based global pivot, first failure wins).
-// One CTA of 512 threads per matrix (blockIdx.x = batch).
+// One CTA of POTF2_THREADS threads per matrix (blockIdx.x = batch).
 // ------------------------------------------------------------------------------------------
+__device__ long long g_potf2_clk[16];     // phase timestamps of the last potf2_inv CTA 0 (inspection)
+constexpr int POTF2_THREADS = 512;
+constexpr int POTF2_WARPS = POTF2_THREADS / 32;
 constexpr int POTF2_LD = 129;
 constexpr int POTF2_PLD = 132;                                   // sub-panel buffer [32][132]
-constexpr int POTF2_SCRATCH = 64 * 68;                           // >= 32*132 and >= 64*(b+4) for b <= 64
-constexpr int POTF2_SMEM_BYTES = (128 * POTF2_LD + POTF2_SCRATCH + 16) * (int)sizeof(double);
+constexpr int POTF2_SCRATCH = 64 * 68;                           // >= 32*132 + 96 and >= 64*(b+4) for b <= 64
+constexpr int POTF2_SMEM_BYTES = (128 * POTF2_LD + POTF2_SCRATCH + 32 * 32 + 16) * (int)sizeof(double);
 
-__global__ void __launch_bounds__(512) potf2_inv_kernel(double* __restrict__ Ablk, int64_t ld, int64_t strideA,
-                                                        double* __restrict__ Dinv, int64_t strideD,
-                                                        int* __restrict__ info, int pivot_base) {
+__global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __restrict__ Ablk, int64_t ld, int64_t strideA,
+                                                                  double* __restrict__ Dinv, int64_t strideD,
+                                                                  int* __restrict__ info, int pivot_base) {
     extern __shared__ __align__(16) double sm[];
     double* sL = sm;                       // [128][129]
     double* sT = sm + 128 * POTF2_LD;      // scratch: sub-panel columns, then T of the inverse levels
@@ -150,62 +153,101 @@ __global__ void __launch_bounds__(512) potf2_inv_kernel(double* __restrict__ Abl
     double* A = Ablk + (int64_t)blockIdx.x * strideA;
     double* Di = Dinv + (int64_t)blockIdx.x * strideD;
     if (tid == 0) s_fail = 0;
-    for (int e = tid; e < 128 * 128; e += 512) {
+    const bool stamp = (tid == 0 && blockIdx.x == 0);
+    if (stamp) g_potf2_clk[0] = clock64();
+    for (int e = tid; e < 128 * 128; e += POTF2_THREADS) {
         int r = e >> 7, c = e & 127;
         sL[r * POTF2_LD + c] = A[(int64_t)r * ld + c];
     }
     __syncthreads();
+    if (stamp) g_potf2_clk[1] = clock64();
 
-    // ---- Cholesky: four 32-column sub-panels.  Column step j (one barrier): every thread reads
-    // the pivot and the still-unscaled column j, forms l_ij = a_ij / sqrt(piv) itself (its own
-    // row i and the <= 31 sub-panel rows c it needs), updates its part of row i inside the
-    // sub-panel and parks l_ij in the panel buffer; the scaled columns are written back to sL
-    // after the sub-panel, followed by a DMMA update of the rest of the block.
-    bool bad = false;
-    for (int sp = 0; sp < 4 && !bad; ++sp) {
+    // ---- Cholesky: four 32-column sub-panels, no block barrier inside the column loop.
+    //  (1) warp 0 factors the 32x32 diagonal block in REGISTERS (lane = row).  Column j of L is
+    //      broadcast through shared memory; the NEXT pivot only needs the lane's own entry
+    //      (a_{j+1,j+1} - l_{j+1,j}^2), so it is formed and shuffled out before the rest of the
+    //      column update: the rsqrt/shuffle latency chain overlaps the update's issue slots.
+    //  (2) warps 1.. solve the rows below against it (lane = row, right-looking substitution,
+    //      L entries broadcast from shared memory) and stage the panel in a conflict-free buffer;
+    //  (3) all warps apply the rank-32 update to the rest of the block with DMMA tiles.
+    double* sRinv = sT + POTF2_SCRATCH - 32;                   // reciprocals of the block's diagonal
+    double* sCol = sT + POTF2_SCRATCH - 96;                    // two 32-entry column buffers (ping-pong)
+    double* sDT = sT + POTF2_SCRATCH;                          // transposed diagonal block [32][32]
+    for (int sp = 0; sp < 4; ++sp) {
         const int c0 = sp * 32, c1 = c0 + 32;
-        const int i = tid & 127, cq = tid >> 7;               // row, column phase (0..3)
-        for (int j = c0; j < c1; ++j) {
-            const double piv = sL[j * POTF2_LD + j];
-            if (!(piv > 0.0)) {                                 // uniform: same value in every thread
-                if (tid == 0) { s_fail = 1; atomicCAS(info + blockIdx.x, 0, pivot_base + j + 1); }
-                bad = true;
-                break;
-            }
-            const double rinv = rsqrt(piv);
-            const double aij = sL[i * POTF2_LD + j];
-            const double lij = (i == j) ? piv * rinv : aij * rinv;
-            double lc[8], v[8];
+        if (warp == 0) {
+            double a[32];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int c = j + 1 + cq + 4 * q;
-                const bool on = (c < c1) && (i >= c);
-                lc[q] = on ? sL[c * POTF2_LD + j] : 0.0;
-                v[q] = on ? sL[i * POTF2_LD + c] : 0.0;
-            }
-            if (cq == 0 && i >= j) sT[(j - c0) * POTF2_PLD + i] = lij;
-            // no hazard inside a step: it reads column j and its own row, and writes only its own
-            // row in columns > j; the single barrier below orders these writes against the next
-            // step's reads of column j + 1
+            for (int c = 0; c < 32; ++c) a[c] = sL[(c0 + lane) * POTF2_LD + c0 + c];
+            int failcol = -1;
+            double d = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int c = j + 1 + cq + 4 * q;
-                if ((c < c1) && (i >= c)) sL[i * POTF2_LD + c] = fma(-lij, lc[q] * rinv, v[q]);
+            for (int j = 0; j < 32; ++j) {
+                if (failcol < 0 && !(d > 0.0)) failcol = j;      // uniform across the warp; keep going
+                const double rinv = rsqrt(d);                    // (garbage after a failure is discarded)
+                const double lj = (lane == j) ? d * rinv : a[j] * rinv;
+                a[j] = lj;
+                if (j < 31) {                                    // next pivot, ahead of the column update
+                    const double own = fma(-lj, lj, a[(j + 1) & 31]);
+                    d = __shfl_sync(0xffffffffu, own, (j + 1) & 31);
+                }
+                if (lane == j) sRinv[j] = rinv;
+                double* col = sCol + (j & 1) * 32;               // column j of L, broadcast through smem
+                col[lane] = lj;
+                __syncwarp();
+                // rows above the diagonal carry garbage that is never consumed: no predicate needed.
+                // Column entries are fetched two at a time (LDS.128).
+#pragma unroll
+                for (int c2 = 0; c2 < 16; ++c2) {
+                    if (2 * c2 + 1 > j) {
+                        const double2 lc = *reinterpret_cast<const double2*>(col + 2 * c2);
+                        if (2 * c2 > j) a[2 * c2] = fma(-lj, lc.x, a[2 * c2]);
+                        a[2 * c2 + 1] = fma(-lj, lc.y, a[2 * c2 + 1]);
+                    }
+                }
             }
-            __syncthreads();
-        }
-        if (bad) break;
-        // scaled sub-panel columns back into sL (rows >= column)
-        for (int e = tid; e < 32 * 128; e += 512) {
-            const int cc = e >> 7, r = e & 127;
-            if (r >= c0 + cc) sL[r * POTF2_LD + c0 + cc] = sT[cc * POTF2_PLD + r];
+            if (failcol >= 0) {
+                if (lane == 0) { s_fail = 1; atomicCAS(info + blockIdx.x, 0, pivot_base + c0 + failcol + 1); }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if (c <= lane) sL[(c0 + lane) * POTF2_LD + c0 + c] = a[c];
+                    sDT[c * 32 + lane] = (c <= lane) ? a[c] : 0.0;      // transposed copy: [column j][row c]
+                }
+            }
         }
         __syncthreads();
+        if (stamp && sp == 0) g_potf2_clk[8] = clock64();
+        if (s_fail) break;
         if (c1 >= 128) break;
-        // trailing update of rows/cols >= c1 with the panel columns [c0, c1): lower 16x16 tiles
+        {   // (2) rows below: x = a * inv(D)^T by substitution
+            const int r = c1 + (warp - 1) * 32 + lane;
+            if (warp >= 1 && r < 128) {
+                double x[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) x[c] = sL[r * POTF2_LD + c0 + c];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    x[j] *= sRinv[j];
+#pragma unroll
+                    for (int c2 = 0; c2 < 16; ++c2) {
+                        if (2 * c2 + 1 > j) {
+                            const double2 lc = *reinterpret_cast<const double2*>(sDT + j * 32 + 2 * c2);
+                            if (2 * c2 > j) x[2 * c2] = fma(-x[j], lc.x, x[2 * c2]);
+                            x[2 * c2 + 1] = fma(-x[j], lc.y, x[2 * c2 + 1]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) { sL[r * POTF2_LD + c0 + c] = x[c]; sT[c * POTF2_PLD + r] = x[c]; }
+            }
+        }
+        __syncthreads();
+        if (stamp && sp == 0) g_potf2_clk[9] = clock64();
+        // (3) trailing update of rows/cols >= c1 with the panel columns [c0, c1): lower 16x16 tiles
         const int nt = (128 - c1) / 16;
         const int ntile = nt * (nt + 1) / 2;
-        for (int t = warp; t < ntile; t += 16) {
+        for (int t = warp; t < ntile; t += POTF2_WARPS) {
             int ti = 0, acc_t = t;
             while (acc_t > ti) { acc_t -= ti + 1; ++ti; }
             const int tj = acc_t;
@@ -233,19 +275,22 @@ __global__ void __launch_bounds__(512) potf2_inv_kernel(double* __restrict__ Abl
                 }
         }
         __syncthreads();
+        if (stamp && sp == 0) g_potf2_clk[10] = clock64();
     }
     __syncthreads();
+    if (stamp) g_potf2_clk[2] = clock64();
     const bool failed = s_fail != 0;
     // write L back (zero strictly-upper part so that later k-ranges may overrun the diagonal tile)
-    for (int e = tid; e < 128 * 128; e += 512) {
+    for (int e = tid; e < 128 * 128; e += POTF2_THREADS) {
         int r = e >> 7, c = e & 127;
         A[(int64_t)r * ld + c] = (c <= r) ? sL[r * POTF2_LD + c] : 0.0;
     }
     if (failed) {                           // leave a harmless identity as the inverse
-        for (int e = tid; e < 128 * 128; e += 512) Di[e] = ((e >> 7) == (e & 127)) ? 1.0 : 0.0;
+        for (int e = tid; e < 128 * 128; e += POTF2_THREADS) Di[e] = ((e >> 7) == (e & 127)) ? 1.0 : 0.0;
         return;
     }
     __syncthreads();
+    if (stamp) g_potf2_clk[3] = clock64();
 
     // ---- inverse, level 0: sixteen 8x8 diagonal blocks, one thread per column
     double x[8];
@@ -267,6 +312,7 @@ __global__ void __launch_bounds__(512) potf2_inv_kernel(double* __restrict__ Abl
         for (int i = 0; i < 8; ++i) sL[(o + i) * POTF2_LD + o + c] = x[i];
     }
     __syncthreads();
+    if (stamp) g_potf2_clk[4] = clock64();
     // ---- levels b = 8 .. 64:  X21 = -X22 * (L21 * X11), both products as DMMA 8x8 tiles that
     //      skip the structurally zero k-ranges; T is staged in scratch with row stride b + 4.
     for (int b = 8; b < 128; b <<= 1) {
@@ -274,39 +320,68 @@ __global__ void __launch_bounds__(512) potf2_inv_kernel(double* __restrict__ Abl
         const int tpp = tb * tb;                         // tiles per pair
         const int ntl = (64 / b) * tpp;                  // tiles over all pairs
         const int ST = b + 4;
-        for (int t = warp; t < ntl; t += 16) {
-            const int pair = t / tpp, rem = t - pair * tpp, ti = rem / tb, tj = rem - ti * tb;
+        // a warp owns a strip of up to four 8x8 tiles in one tile row (shared A fragment, four
+        // independent DMMA chains: the ~100-cycle DMMA latency is hidden by ILP, not by warps)
+        const int tjg_n = (tb + 3) >> 2;                 // strips per tile row
+        const int nstrip = (64 / b) * tb * tjg_n;
+        for (int g = warp; g < nstrip; g += POTF2_WARPS) {
+            const int pair = g / (tb * tjg_n), rem = g - pair * (tb * tjg_n), ti = rem / tjg_n, tj0 = (rem - ti * tjg_n) * 4;
             const int o = pair * 2 * b;
-            double c0a = 0.0, c1a = 0.0;
-            for (int k = tj * 8; k < b; k += 4) {        // X11[k][n] = 0 for k < n
-                const double a = sL[(o + b + ti * 8 + fr) * POTF2_LD + o + k + fk];
-                const double bv = sL[(o + k + fk) * POTF2_LD + o + tj * 8 + fr];
-                dmma8x8x4(c0a, c1a, a, bv);
+            double cc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+            const double* arow = sL + (o + b + ti * 8 + fr) * POTF2_LD + o + fk;
+            for (int k = tj0 * 8; k < b; k += 4) {       // X11[k][n] = 0 for k < n
+                const double a = arow[k];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (tj0 + q < tb && k >= (tj0 + q) * 8) {
+                        const double bv = sL[(o + k + fk) * POTF2_LD + o + (tj0 + q) * 8 + fr];
+                        dmma8x8x4(cc[q][0], cc[q][1], a, bv);
+                    }
+                }
             }
-            double* dst = sT + pair * b * ST + (ti * 8 + fr) * ST + tj * 8 + 2 * fk;
-            dst[0] = c0a;
-            dst[1] = c1a;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (tj0 + q < tb) {
+                    double* dst = sT + pair * b * ST + (ti * 8 + fr) * ST + (tj0 + q) * 8 + 2 * fk;
+                    dst[0] = cc[q][0];
+                    dst[1] = cc[q][1];
+                }
+            }
         }
         __syncthreads();
-        for (int t = warp; t < ntl; t += 16) {
-            const int pair = t / tpp, rem = t - pair * tpp, ti = rem / tb, tj = rem - ti * tb;
+        for (int g = warp; g < nstrip; g += POTF2_WARPS) {
+            const int pair = g / (tb * tjg_n), rem = g - pair * (tb * tjg_n), ti = rem / tjg_n, tj0 = (rem - ti * tjg_n) * 4;
             const int o = pair * 2 * b;
-            double c0a = 0.0, c1a = 0.0;
+            double cc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+            const double* arow = sL + (o + b + ti * 8 + fr) * POTF2_LD + o + b + fk;
+            const double* tcol = sT + pair * b * ST + fk * ST + fr;
             for (int k = 0; k < (ti + 1) * 8; k += 4) {  // X22[m][k] = 0 for k > m
-                const double a = sL[(o + b + ti * 8 + fr) * POTF2_LD + o + b + k + fk];
-                const double bv = sT[pair * b * ST + (k + fk) * ST + tj * 8 + fr];
-                dmma8x8x4(c0a, c1a, a, bv);
+                const double a = arow[k];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (tj0 + q < tb) {
+                        const double bv = tcol[k * ST + (tj0 + q) * 8];
+                        dmma8x8x4(cc[q][0], cc[q][1], a, bv);
+                    }
+                }
             }
-            double* dst = sL + (o + b + ti * 8 + fr) * POTF2_LD + o + tj * 8 + 2 * fk;
-            dst[0] = -c0a;
-            dst[1] = -c1a;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (tj0 + q < tb) {
+                    double* dst = sL + (o + b + ti * 8 + fr) * POTF2_LD + o + (tj0 + q) * 8 + 2 * fk;
+                    dst[0] = -cc[q][0];
+                    dst[1] = -cc[q][1];
+                }
+            }
         }
         __syncthreads();
     }
-    for (int e = tid; e < 128 * 128; e += 512) {
+    if (stamp) g_potf2_clk[5] = clock64();
+    for (int e = tid; e < 128 * 128; e += POTF2_THREADS) {
         int r = e >> 7, c = e & 127;
         Di[e] = (c <= r) ? sL[r * POTF2_LD + c] : 0.0;
     }
+    if (stamp) g_potf2_clk[6] = clock64();
 }
 
 // copy the T diagonal-block inverses into the diagonal tiles of Linv

@@ -71,6 +71,10 @@ int32_t abo_ctx_launch_count(const abo_ctx* ctx, int64_t* count);
 int32_t abo_ctx_profile(abo_ctx* ctx, int32_t enable);
 int32_t abo_ctx_profile_read(abo_ctx* ctx, double ms[3], int64_t launches[3]);
 
+/* inspection: SM-clock timestamps of the phases of the last diagonal-block factorisation kernel
+ * (load, factor, store L, inverse level 0, inverse levels, store) — tools/potrf_probe.py */
+int32_t abo_debug_potf2_clocks(abo_ctx* ctx, int64_t out[16]);
+
 /* ---- surrogate: struct StandardGP / GradientGP (src/surrogates/StandardGP.jl:11-16,
  *      GradientGP.jl:17-22).  p = 1 (StandardGP) or d + 1 (GradientGP). --------------------- */
 int32_t abo_gp_create(abo_ctx* ctx, int32_t kernel_id, int32_t d, int32_t p, abo_gp** out);

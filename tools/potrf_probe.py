@@ -21,4 +21,6 @@ for n in sizes:
     fl = n ** 3 / 3 + n ** 2 / 2
     L = torch.tril(A)
     err = (torch.linalg.norm(L @ L.T - K0) / torch.linalg.norm(K0)).item()
+    ck = ctx.potf2_clocks(); names = ["load", "factor", "storeL", "inv0", "invL", "storeD"]
+    print("   potf2 phases (cycles):", {names[i]: ck[i + 1] - ck[i] for i in range(6)}, "total", ck[6] - ck[0], "| sub-panel 0: diag", ck[8] - ck[1], "trsm", ck[9] - ck[8], "update", ck[10] - ck[9])
     print(f"n={n} potrf {best:.3f} ms  {fl / best / 1e9:.2f} TFLOP/s  relres={err:.2e}", flush=True)
