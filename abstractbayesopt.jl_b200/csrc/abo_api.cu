@@ -48,11 +48,14 @@ static int configure_kernels() {
     CU(configure_gemm<KC, MC, EPI_STORE>());
     CU(configure_gemm<MC, MC, EPI_STORE>());
     CU(configure_gemm<KC, KC, EPI_SUMSQ>());
-    CU(cudaFuncSetAttribute(gemm_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<64>::SMEM_BYTES));
-    CU(cudaFuncSetAttribute(gemm_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<32>::SMEM_BYTES));
+    CU(cudaFuncSetAttribute(gemm_small_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<32, 4>::SMEM_BYTES));
+    CU(cudaFuncSetAttribute(gemm_small_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<32, 8>::SMEM_BYTES));
+    CU(cudaFuncSetAttribute(gemm_small_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<64, 8>::SMEM_BYTES));
     CU(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(potf2_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_BYTES));
     CU(cudaFuncSetAttribute(sweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
-    CU(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(syrk_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
     return ABO_OK;
 }
 
@@ -265,6 +268,20 @@ int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strid
     return ABO_OK;
 }
 
+// launch with programmatic stream serialization (PDL): the kernel may become resident while its
+// predecessor in the stream drains; the kernels call griddepcontrol.wait before touching memory
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ------------------------------------------------------------------------------------------
 // Single-matrix Cholesky with two-level blocking and look-ahead (the "Cholesky TFLOP/s" path).
 //   outer block = OB tile columns (512): inside it the panels are factored right-looking
@@ -276,8 +293,14 @@ int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strid
 // ------------------------------------------------------------------------------------------
 int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Dinv, int* info) {
     const int T = (int)(Npad / NB);
-    static const int OB_env = getenv("ABO_POTRF_OB") ? atoi(getenv("ABO_POTRF_OB")) : 4;
+    static const int OB_env = getenv("ABO_POTRF_OB") ? atoi(getenv("ABO_POTRF_OB")) : 3;
     static const bool one_stream = getenv("ABO_POTRF_1STREAM") != nullptr;
+    static const bool use_ws = getenv("ABO_POTF2_V6") == nullptr;
+    static const bool pdl_on = getenv("ABO_NO_PDL") == nullptr;
+    static const bool ramp = getenv("ABO_POTRF_NORAMP") == nullptr;
+    static const int reserve = getenv("ABO_POTRF_RESERVE") ? atoi(getenv("ABO_POTRF_RESERVE")) : -1;
+    // panel GEMMs: 64-row tiles while the panel is tall (throughput), 32-row tiles once it is short (latency)
+    static const int big_rem = getenv("ABO_POTRF_BIGREM") ? atoi(getenv("ABO_POTRF_BIGREM")) : 4096;
     const int OB = std::max(1, OB_env);
     if (T <= OB) return potrf_blocked(c, A, Npad, ld, 0, Dinv, 0, info, 1);
     cudaStream_t sp = c->stream, su = one_stream ? c->stream : c->stream2;
@@ -287,13 +310,25 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
     CU(cudaEventRecord(c->ev_a, sp));                 // su must see everything enqueued on sp so far
     CU(cudaStreamWaitEvent(su, c->ev_a, 0));
     bool rest_pending = false;
-    for (int Jb = 0; Jb < T; Jb += OB) {
-        const int je = std::min(Jb + OB, T);
+    static const bool trace = getenv("ABO_POTRF_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;           // per outer block: start, panel done, U_next done (sp), U_rest start, done (su)
+    auto mark = [&](cudaStream_t s_) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); tev.push_back(e); } };
+    mark(sp);
+    // outer blocks ramp up (1, 2, OB, OB, ...): the first panels are not hidden behind any update, so
+    // the trailing-update stream is given work as early as possible
+    int step = 0;
+    for (int Jb = 0, je = 0; Jb < T; Jb = je, ++step) {
+        je = std::min(Jb + (ramp ? std::min(step + 1, OB) : OB), T);
+        // PDL only once the trailing matrix is small: early-resident dependents would otherwise take
+        // shared memory away from the big trailing-update CTAs of the second stream
+        const bool pdl = pdl_on && (T - Jb) <= 12;
         // ---- panel block: tile columns [Jb, je)
+        mark(sp);
         for (int jp = Jb; jp < je; ++jp) {
             double* Ajj = A + (int64_t)jp * NB * (ld + 1);
             double* Dj = Dinv + (int64_t)jp * NB * NB;
-            potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM_BYTES, sp>>>(Ajj, ld, 0, Dj, 0, info, jp * NB);
+            if (use_ws) CU(launch_pdl(potf2_ws_kernel, dim3(1), dim3(512), PW_SMEM_BYTES, sp, pdl, Ajj, ld, (int64_t)0, Dj, (int64_t)0, info, jp * NB));
+            else potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM_BYTES, sp>>>(Ajj, ld, 0, Dj, 0, info, jp * NB);
             KL(c);
             const int rem = (T - jp - 1) * NB;
             if (rem <= 0) break;
@@ -301,7 +336,8 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
             GemmParams g{};
             g.A = P; g.lda = ld; g.B = Dj; g.ldb = NB; g.C = P; g.ldc = ld;
             g.M = rem; g.N = NB; g.K = NB; g.alpha = 1.0; g.beta = 0.0; g.flags = 0;
-            CU(launch_gemm_small<32>(g, 1, sp));
+            if (rem >= big_rem) CU(launch_pdl(gemm_small_kernel<64, 8>, dim3(g.N / BN, g.M / 64, 1), dim3(256), GemmS<64, 8>::SMEM_BYTES, sp, pdl, g));
+            else CU(launch_pdl(gemm_small_kernel<32, 8>, dim3(g.N / BN, g.M / 32, 1), dim3(256), GemmS<32, 8>::SMEM_BYTES, sp, pdl, g));
             KL(c);
             const int ncol = (je - jp - 1) * NB;       // remaining columns of this outer block
             if (ncol > 0) {
@@ -309,31 +345,51 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
                 s.A = P; s.lda = ld; s.B = P; s.ldb = ld;
                 s.C = Ajj + (int64_t)NB * (ld + 1); s.ldc = ld;
                 s.M = rem; s.N = ncol; s.K = NB; s.alpha = -1.0; s.beta = 1.0; s.flags = LOWER_ONLY;
-                CU(launch_gemm_small<32>(s, 1, sp));
+                if (rem >= big_rem) CU(launch_pdl(gemm_small_kernel<64, 8>, dim3(s.N / BN, s.M / 64, 1), dim3(256), GemmS<64, 8>::SMEM_BYTES, sp, pdl, s));
+                else CU(launch_pdl(gemm_small_kernel<32, 8>, dim3(s.N / BN, s.M / 32, 1), dim3(256), GemmS<32, 8>::SMEM_BYTES, sp, pdl, s));
                 KL(c);
             }
         }
+        mark(sp);
         if (je >= T) break;
         SyrkParams u;
         u.C = A; u.ld = ld; u.kcol0 = Jb * NB; u.nk = (je - Jb) * (NB / 16);
         // ---- U_rest(b) on the second stream: needs panel(b) (event) and, by stream order, U_rest(b-1)
-        const int jn = std::min(je + OB, T);
+        const int jn = std::min(je + (ramp ? std::min(step + 2, OB) : OB), T);
         CU(cudaEventRecord(c->ev_a, sp));
         if (jn < T) {
             CU(cudaStreamWaitEvent(su, c->ev_a, 0));
             u.row_t0 = jn; u.col_t0 = jn;
-            syrk_tma_kernel<<<dim3(T - jn, T - jn), SW_THREADS, SW_SMEM_BYTES, su>>>(tmL, u);
+            mark(su);
+            if (reserve >= 0) {      // persistent U_rest on (SMs - reserve) CTAs; the panel stream keeps the rest
+                SyrkPersistParams up;
+                up.C = A; up.ld = ld; up.t0 = jn; up.T = T; up.kcol0 = u.kcol0; up.nk = u.nk;
+                const int ntl = (T - jn) * (T - jn + 1) / 2;
+                const int grid = std::max(1, std::min(ntl, c->sms - reserve));
+                syrk_persist_kernel<<<grid, SW_THREADS, SW_SMEM_BYTES, su>>>(tmL, up);
+            } else {
+                syrk_tma_kernel<<<dim3(T - jn, T - jn), SW_THREADS, SY_SMEM_BYTES, su>>>(tmL, u);
+            }
             KL(c);
+            mark(su);
         }
         // ---- U_next(b) on the panel stream: the next block's columns; they were last touched by
         //      U_rest(b-1), so wait for it
         if (rest_pending) CU(cudaStreamWaitEvent(sp, c->ev_b, 0));
         u.row_t0 = je; u.col_t0 = je;
-        syrk_tma_kernel<<<dim3(jn - je, T - je), SW_THREADS, SW_SMEM_BYTES, sp>>>(tmL, u);
+        CU(launch_pdl(syrk_tma_kernel, dim3(jn - je, T - je), dim3(SW_THREADS), SY_SMEM_BYTES, sp, pdl && !rest_pending, tmL, u));
         KL(c);
+        mark(sp);
         if (jn < T) { CU(cudaEventRecord(c->ev_b, su)); rest_pending = true; }
     }
     if (rest_pending) CU(cudaStreamWaitEvent(sp, c->ev_b, 0));
+    if (trace) {
+        cudaStreamSynchronize(sp); cudaStreamSynchronize(su);
+        fprintf(stderr, "potrf trace (ms since start), %zu events:", tev.size());
+        for (size_t i = 1; i < tev.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[i]); fprintf(stderr, " %.3f", ms); }
+        fprintf(stderr, "\n");
+        for (auto e : tev) cudaEventDestroy(e);
+    }
     return ABO_OK;
 }
 

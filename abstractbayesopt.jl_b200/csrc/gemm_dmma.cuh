@@ -53,6 +53,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// programmatic dependent launch (PDL): let the next kernel of the stream get resident early, and
+// wait for the previous kernel's results before touching global memory.  Both are no-ops for a
+// kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -201,26 +207,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmParams p
 // K = 128): 2x / 4x as many CTAs, half / quarter of the time per tile.
 // 8 warps as (BMT/32) along M x (256/BMT) along N, warp tile 32 x (BMT/2).
 // ------------------------------------------------------------------------------------------
-template <int BMT>
+template <int BMT, int NW>
 struct GemmS {
-    static constexpr int WM = BMT / 32, WN = 8 / WM, WNC = 128 / WN, NT = WNC / 8;
+    static constexpr int THREADS = NW * 32;
+    static constexpr int WM = BMT / 32, WN = NW / WM, WNC = 128 / WN, NT = WNC / 8;
     static constexpr int A_DOUBLES = 4 * BMT * 4, B_DOUBLES = 4 * 128 * 4;
     static constexpr int SMEM_BYTES = STAGES * (A_DOUBLES + B_DOUBLES) * (int)sizeof(double);
 };
 
-template <int BMT>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_small_kernel(GemmParams p) {
-    using S = GemmS<BMT>;
+// NW = 4 warps keeps a 32-row CTA at 128 threads / <= 16K registers / 80 KB shared memory, small
+// enough to be co-resident with a trailing-update CTA of the look-ahead stream on the same SM.
+template <int BMT, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 2) gemm_small_kernel(GemmParams p) {
+    using S = GemmS<BMT, NW>;
     extern __shared__ __align__(16) double smem[];
     double* sA = smem;
     double* sB = smem + STAGES * S::A_DOUBLES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp % S::WM) * 32, wn = (warp / S::WM) * S::WNC;
     const int m0 = blockIdx.y * BMT, n0 = blockIdx.x * BN;
+    pdl_launch_dependents();
     if ((p.flags & LOWER_ONLY) && n0 > m0) return;
     const double* A = p.A + (int64_t)blockIdx.z * p.strideA;
     const double* B = p.B + (int64_t)blockIdx.z * p.strideB;
     const int nk = p.K / BK;
+    pdl_wait();
 
     double acc[4][S::NT][2];
 #pragma unroll
@@ -231,14 +242,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_small_kernel(GemmParams 
     auto load_stage = [&](int s, int kt) {
         const int k0 = kt * BK;
 #pragma unroll
-        for (int q = 0; q < BMT / 32; ++q) {              // A: BMT rows x 8 chunks of 16 B
-            int c = tid + GEMM_THREADS * q, row = c >> 3, ch = c & 7;
+        for (int q = 0; q < BMT * 8 / S::THREADS; ++q) {   // A: BMT rows x 8 chunks of 16 B
+            int c = tid + S::THREADS * q, row = c >> 3, ch = c & 7;
             cp_async16(sA + s * S::A_DOUBLES + (((ch >> 1) * BMT + row) << 2) + ((ch & 1) << 1),
                        A + (int64_t)(m0 + row) * p.lda + k0 + 2 * ch);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {                     // B: 128 rows x 8 chunks
-            int c = tid + GEMM_THREADS * q, row = c >> 3, ch = c & 7;
+        for (int q = 0; q < 1024 / S::THREADS; ++q) {      // B: 128 rows x 8 chunks
+            int c = tid + S::THREADS * q, row = c >> 3, ch = c & 7;
             cp_async16(sB + s * S::B_DOUBLES + (((ch >> 1) * 128 + row) << 2) + ((ch & 1) << 1),
                        B + (int64_t)(n0 + row) * p.ldb + k0 + 2 * ch);
         }
@@ -291,14 +302,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_small_kernel(GemmParams 
             *dst = v;
         }
     }
-}
-
-template <int BMT>
-inline cudaError_t launch_gemm_small(const GemmParams& p, int batch, cudaStream_t st) {
-    if (p.M <= 0 || p.N <= 0 || batch <= 0) return cudaSuccess;
-    dim3 grid(p.N / BN, p.M / BMT, batch);
-    gemm_small_kernel<BMT><<<grid, GEMM_THREADS, GemmS<BMT>::SMEM_BYTES, st>>>(p);
-    return cudaGetLastError();
 }
 
 template <int LA, int LB, int EPI>

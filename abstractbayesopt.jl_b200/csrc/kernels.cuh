@@ -384,6 +384,259 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
     if (stamp) g_potf2_clk[6] = clock64();
 }
 
+// ------------------------------------------------------------------------------------------
+// potf2_ws_kernel — warp-specialised version of the diagonal-block kernel: the FACTOR group
+// (warps 0-7) runs the Cholesky of the 128 x 128 block exactly as potf2_inv_kernel does, while
+// the INVERSE group (warps 8-15) builds L^-1 one 32-row block behind it:
+//     round s (after the diagonal block D_s is final):
+//        X_ss = inv(D_s)                              (8x8 scalar level + two DMMA levels)
+//        S_st = sum_{u=t}^{s-1} L_su X_ut   (t < s)   (DMMA, X_ut read back from global Dinv)
+//        X_st = - X_ss S_st                           (DMMA)  -> global Dinv
+// so that when the last diagonal block is done only X_33 and one multiply remain, overlapped with
+// the write-back of L.  Groups synchronise internally with named barriers (1: factor, 2: inverse);
+// the factor group never waits for the inverse group: it only ARRIVES on per-round barriers
+// (4+s: D_s final, 8+s: rows below column block s final) that the inverse group syncs on.
+// ------------------------------------------------------------------------------------------
+constexpr int PW_XLD = 36;
+constexpr int PW_F_SCRATCH = 32 * POTF2_PLD + 64 + 32 + 32 * 32;            // panel | col ping-pong | 1/diag | D^T
+constexpr int PW_I_SCRATCH = 32 * PW_XLD + 3 * 32 * PW_XLD + 320;            // X_ss | S_s0..S_s2 | T of the 32-block levels
+constexpr int PW_SMEM_BYTES = (128 * POTF2_LD + PW_F_SCRATCH + PW_I_SCRATCH + 16) * (int)sizeof(double);
+
+__device__ __forceinline__ void bar_named(int id, int count) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+
+__global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk, int64_t ld, int64_t strideA,
+                                                       double* __restrict__ Dinv, int64_t strideD,
+                                                       int* __restrict__ info, int pivot_base) {
+    extern __shared__ __align__(16) double sm[];
+    double* sL = sm;                                   // [128][129]
+    double* sP = sm + 128 * POTF2_LD;                  // factor group: panel [32][132]
+    double* sCol = sP + 32 * POTF2_PLD;                // two 32-entry column buffers
+    double* sRinv = sCol + 64;                         // reciprocals of the current block's diagonal
+    double* sDT = sRinv + 32;                          // transposed diagonal block [32][32]
+    double* sXs = sDT + 32 * 32;                       // inverse group: X_ss [32][36]
+    double* sS = sXs + 32 * PW_XLD;                    // S_st, t = 0..2, [32][36] each
+    double* sTi = sS + 3 * 32 * PW_XLD;                // T staging of the levels inside a 32-block
+    __shared__ int s_fail;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
+    double* A = Ablk + (int64_t)blockIdx.x * strideA;
+    double* Di = Dinv + (int64_t)blockIdx.x * strideD;
+    if (tid == 0) s_fail = 0;
+    pdl_launch_dependents();
+    pdl_wait();
+    const bool stamp = (tid == 0 && blockIdx.x == 0);
+    if (stamp) g_potf2_clk[0] = clock64();
+    for (int e = tid; e < 128 * 128; e += 512) {
+        int r = e >> 7, c = e & 127;
+        sL[r * POTF2_LD + c] = A[(int64_t)r * ld + c];
+    }
+    __syncthreads();
+    if (stamp) g_potf2_clk[1] = clock64();
+
+    if (warp < 8) {
+        // =============================== FACTOR GROUP ===============================
+        for (int sp = 0; sp < 4; ++sp) {
+            const int c0 = sp * 32, c1 = c0 + 32;
+            if (warp == 0) {
+                double a[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) a[c] = sL[(c0 + lane) * POTF2_LD + c0 + c];
+                int failcol = -1;
+                double d = __shfl_sync(0xffffffffu, a[0], 0);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (failcol < 0 && !(d > 0.0)) failcol = j;
+                    const double rinv = rsqrt(d);
+                    const double lj = (lane == j) ? d * rinv : a[j] * rinv;
+                    a[j] = lj;
+                    if (j < 31) {
+                        const double own = fma(-lj, lj, a[(j + 1) & 31]);
+                        d = __shfl_sync(0xffffffffu, own, (j + 1) & 31);
+                    }
+                    if (lane == j) sRinv[j] = rinv;
+                    double* col = sCol + (j & 1) * 32;
+                    col[lane] = lj;
+                    __syncwarp();
+#pragma unroll
+                    for (int c2 = 0; c2 < 16; ++c2) {
+                        if (2 * c2 + 1 > j) {
+                            const double2 lc = *reinterpret_cast<const double2*>(col + 2 * c2);
+                            if (2 * c2 > j) a[2 * c2] = fma(-lj, lc.x, a[2 * c2]);
+                            a[2 * c2 + 1] = fma(-lj, lc.y, a[2 * c2 + 1]);
+                        }
+                    }
+                }
+                if (failcol >= 0) {
+                    if (lane == 0) { s_fail = 1; atomicCAS(info + blockIdx.x, 0, pivot_base + c0 + failcol + 1); }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        // the block's strictly-upper part is zeroed: the inverse group reads it as a full tile
+                        sL[(c0 + lane) * POTF2_LD + c0 + c] = (c <= lane) ? a[c] : 0.0;
+                        sDT[c * 32 + lane] = (c <= lane) ? a[c] : 0.0;
+                    }
+                }
+            }
+            bar_named(1, 256);                             // D_sp is final for the factor group ...
+            asm volatile("bar.arrive %0, 512;\n" ::"r"(4 + sp) : "memory");   // ... and signalled to the inverse group (never waits for it)
+            if (s_fail) break;
+            if (c1 >= 128) break;
+            {
+                const int r = c1 + (warp - 1) * 32 + lane;
+                if (warp >= 1 && r < 128) {
+                    double x[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) x[c] = sL[r * POTF2_LD + c0 + c];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        x[j] *= sRinv[j];
+#pragma unroll
+                        for (int c2 = 0; c2 < 16; ++c2) {
+                            if (2 * c2 + 1 > j) {
+                                const double2 lc = *reinterpret_cast<const double2*>(sDT + j * 32 + 2 * c2);
+                                if (2 * c2 > j) x[2 * c2] = fma(-x[j], lc.x, x[2 * c2]);
+                                x[2 * c2 + 1] = fma(-x[j], lc.y, x[2 * c2 + 1]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) { sL[r * POTF2_LD + c0 + c] = x[c]; sP[c * POTF2_PLD + r] = x[c]; }
+                }
+            }
+            bar_named(1, 256);
+            asm volatile("bar.arrive %0, 512;\n" ::"r"(8 + sp) : "memory");   // rows below column block sp are final: inverse group may read them
+            const int nt = (128 - c1) / 16;
+            const int ntile = nt * (nt + 1) / 2;
+            for (int t = warp; t < ntile; t += 8) {
+                int ti = 0, acc_t = t;
+                while (acc_t > ti) { acc_t -= ti + 1; ++ti; }
+                const int tj = acc_t;
+                const int r0 = c1 + 16 * ti, q0 = c1 + 16 * tj;
+                double cacc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    double a[2], b[2];
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi) a[mi] = sP[(4 * kk + fk) * POTF2_PLD + r0 + 8 * mi + fr];
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni) b[ni] = sP[(4 * kk + fk) * POTF2_PLD + q0 + 8 * ni + fr];
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 2; ++ni) dmma8x8x4(cacc[mi][ni][0], cacc[mi][ni][1], a[mi], b[ni]);
+                }
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni) {
+                        double* dst = sL + (r0 + 8 * mi + fr) * POTF2_LD + q0 + 8 * ni + 2 * fk;
+                        dst[0] -= cacc[mi][ni][0];
+                        dst[1] -= cacc[mi][ni][1];
+                    }
+            }
+            bar_named(1, 256);
+        }
+        if (stamp) g_potf2_clk[2] = clock64();
+        // write L back while the inverse group finishes its last round
+        if (!s_fail) {
+            for (int e = tid; e < 128 * 128; e += 256) {
+                int r = e >> 7, c = e & 127;
+                A[(int64_t)r * ld + c] = (c <= r) ? sL[r * POTF2_LD + c] : 0.0;
+            }
+        }
+        if (stamp) g_potf2_clk[3] = clock64();
+    } else {
+        // =============================== INVERSE GROUP ===============================
+        const int it = tid - 256, iw = warp - 8;
+        for (int e = it; e < 128 * 128; e += 256) {          // strictly-upper 32-blocks of the result are zero
+            int r = e >> 7, c = e & 127;
+            if ((c >> 5) > (r >> 5)) Di[e] = 0.0;
+        }
+        for (int s = 0; s < 4; ++s) {
+            const int c0 = s * 32;
+            if (s > 0) {
+                // ---- (ahead of the hand-off) S_st = sum_{u=t}^{s-1} L_su X_ut : strips (t, ti) of four
+                //      8x8 tiles; needs X rows < s (this group) and L_s,u<s (factor group: barrier 3)
+                bar_named(8 + s - 1, 512);
+                for (int g = iw; g < 4 * s; g += 8) {
+                    const int t = g >> 2, ti = g & 3;
+                    double cc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+                    const double* arow = sL + (c0 + ti * 8 + fr) * POTF2_LD + fk;
+                    for (int k = 32 * t; k < c0; k += 4) {
+                        const double a = arow[k];
+                        const double* brow = Di + (k + fk) * 128 + 32 * t + fr;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) dmma8x8x4(cc[q][0], cc[q][1], a, brow[q * 8]);   // written by this CTA (same SM, same L1)
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        double* dst = sS + t * 32 * PW_XLD + (ti * 8 + fr) * PW_XLD + q * 8 + 2 * fk;
+                        dst[0] = cc[q][0]; dst[1] = cc[q][1];
+                    }
+                }
+            }
+            bar_named(4 + s, 512);                         // hand-off: D_s is final (factor group only arrives)
+            if (s_fail) break;
+            // ---- X_ss = inv(D_s) by ONE warp, no barriers: lane = column c of the inverse, right-looking
+            //      substitution  x_j = acc_j / L_jj ; acc_i -= L_ij x_j (i > j)  with L broadcast from sL.
+            //      Columns left of c come out as exact zeros (acc_j = 0 for j < c).
+            if (iw == 0) {
+                sTi[lane] = 1.0 / sL[(c0 + lane) * POTF2_LD + c0 + lane];
+                __syncwarp();
+                double acc[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const double xj = acc[j] * sTi[j];
+                    acc[j] = xj;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i > j) acc[i] = fma(-sL[(c0 + i) * POTF2_LD + c0 + j], xj, acc[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sXs[i * PW_XLD + lane] = acc[i];
+            }
+            bar_named(2, 256);
+            for (int e = it; e < 32 * 32; e += 256) {          // X_ss -> global (upper part is zero)
+                int r = e >> 5, c = e & 31;
+                Di[(c0 + r) * 128 + c0 + c] = sXs[r * PW_XLD + c];
+            }
+            if (s > 0) {
+                // ---- X_st = - X_ss S_st  -> global
+                for (int g = iw; g < 4 * s; g += 8) {
+                    const int t = g >> 2, ti = g & 3;
+                    double cc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+                    const double* arow = sXs + (ti * 8 + fr) * PW_XLD + fk;
+                    const double* bcol = sS + t * 32 * PW_XLD + fk * PW_XLD + fr;
+                    for (int k = 0; k < (ti + 1) * 8; k += 4) {
+                        const double a = arow[k];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) dmma8x8x4(cc[q][0], cc[q][1], a, bcol[k * PW_XLD + q * 8]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        double* dst = Di + (c0 + ti * 8 + fr) * 128 + 32 * t + q * 8 + 2 * fk;
+                        dst[0] = -cc[q][0]; dst[1] = -cc[q][1];
+                    }
+                }
+            }
+            bar_named(2, 256);                               // sXs / sS free for the next round
+        }
+    }
+    __syncthreads();
+    if (s_fail) {                                            // harmless identity as the inverse
+        for (int e = tid; e < 128 * 128; e += 512) Di[e] = ((e >> 7) == (e & 127)) ? 1.0 : 0.0;
+        for (int e = tid; e < 128 * 128; e += 512) {
+            int r = e >> 7, c = e & 127;
+            A[(int64_t)r * ld + c] = (c <= r) ? sL[r * POTF2_LD + c] : 0.0;
+        }
+    }
+    if (stamp) g_potf2_clk[6] = clock64();
+}
+
 // copy the T diagonal-block inverses into the diagonal tiles of Linv
 __global__ void place_diag_kernel(const double* __restrict__ Dinv, double* __restrict__ Linv, int64_t ld,
                                   int64_t strideD, int64_t strideL) {
