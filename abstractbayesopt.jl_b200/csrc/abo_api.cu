@@ -83,6 +83,10 @@ extern "C" int32_t abo_ctx_create(int32_t device, abo_ctx** out) {
     CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));   // look-ahead trailing updates
     CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+    for (int q = 0; q < 2; ++q) {
+        CU(cudaEventCreateWithFlags(&c->ev_ks[q], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_sw[q], cudaEventDisableTiming));
+    }
     int rc = configure_kernels();
     if (rc) return rc;
     *out = c;
@@ -99,6 +103,7 @@ extern "C" int32_t abo_ctx_destroy(abo_ctx* c) {
     abo_nccl_teardown(c);
     cudaEventDestroy(c->ev_a);
     cudaEventDestroy(c->ev_b);
+    for (int q = 0; q < 2; ++q) { cudaEventDestroy(c->ev_ks[q]); cudaEventDestroy(c->ev_sw[q]); }
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->stream2);
     delete c;
@@ -665,12 +670,12 @@ extern "C" int32_t abo_gp_factor(const abo_gp* g, int32_t which, double* out) {
 // ------------------------------------------------------------------------------------------
 template <int DT>
 static void launch_ks(abo_ctx* c, const abo_gp* g, const double* dXc, int64_t c_begin, int64_t m_total, int bo,
-                      double* Ks, double* pmean, int64_t mc_eff, int64_t mc, int npb) {
+                      double* Ks, double* pmean, int64_t mc_eff, int64_t mc, int npb, cudaStream_t stream) {
     if (g->p == 1)
-        ks_build_kernel<DT, false><<<dim3(npb, (unsigned)(mc_eff / KS_CB)), 128, 0, c->stream>>>(
+        ks_build_kernel<DT, false><<<dim3(npb, (unsigned)(mc_eff / KS_CB)), 128, 0, stream>>>(
             gp_spec(g), g->dXsT, g->ldx, g->n, g->N, g->Npad, g->dAlpha, dXc, c_begin, m_total, bo, Ks, pmean, mc);
     else
-        ks_build_kernel<DT, true><<<dim3(npb, (unsigned)(mc_eff / KS_CB)), 128, 0, c->stream>>>(
+        ks_build_kernel<DT, true><<<dim3(npb, (unsigned)(mc_eff / KS_CB)), 128, 0, stream>>>(
             gp_spec(g), g->dXsT, g->ldx, g->n, g->N, g->Npad, g->dAlpha, dXc, c_begin, m_total, bo, Ks, pmean, mc);
 }
 
@@ -702,15 +707,26 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
     mc = std::min<int64_t>(mc, (m + NB - 1) / NB * NB);
     const int64_t vpts = (Npad + g->p - 1) / g->p;                 // virtual points incl. padding columns
     const int npb = (int)((vpts + 127) / 128);
-    double *Ks, *pmean, *sumsq;
+    // Optional (ABO_SWEEP_OVERLAP=1): the K* tile builder of chunk i+1 on the second stream while the
+    // DMMA contraction of chunk i runs, two K* / mean-partial buffers ping-ponging.  Measured on B200:
+    // 514.5k vs 513.9k candidates/s — no gain, DMMA and DFMA share the FP64 datapath — so it is off by
+    // default (it doubles the K* workspace).
+    const int64_t nchunks = (m + mc - 1) / mc;
+    static const bool want_overlap = getenv("ABO_SWEEP_OVERLAP") != nullptr;
+    const bool overlap = !use_v1 && !c->profile && nchunks > 1 && want_overlap;
+    const int nbuf = overlap ? 2 : 1;
+    double *KsAll, *pmeanAll, *sumsq;
     int rc;
-    if ((rc = ws_get(c, WS_KS, sizeof(double) * (size_t)mc * Npad, (void**)&Ks))) return rc;
-    if ((rc = ws_get(c, WS_PMEAN, sizeof(double) * (size_t)npb * mc, (void**)&pmean))) return rc;
+    if ((rc = ws_get(c, WS_KS, sizeof(double) * (size_t)mc * Npad * nbuf, (void**)&KsAll))) return rc;
+    if ((rc = ws_get(c, WS_PMEAN, sizeof(double) * (size_t)npb * mc * nbuf, (void**)&pmeanAll))) return rc;
     if ((rc = ws_get(c, WS_SUMSQ, sizeof(double) * (size_t)T * mc, (void**)&sumsq))) return rc;
-    CUtensorMap tmA, tmB;
+    double* KsB[2] = {KsAll, KsAll + (size_t)mc * Npad * (nbuf - 1)};
+    double* pmB[2] = {pmeanAll, pmeanAll + (size_t)npb * mc * (nbuf - 1)};
+    CUtensorMap tmA, tmB[2];
     if (!use_v1) {
         if ((rc = make_tmap_k4(&tmA, g->dLinv, Npad, Npad, g->ld))) return rc;
-        if ((rc = make_tmap_k4(&tmB, Ks, Npad, mc, Npad))) return rc;
+        for (int q = 0; q < nbuf; ++q)
+            if ((rc = make_tmap_k4(&tmB[q], KsB[q], Npad, mc, Npad))) return rc;
     }
     AcqSpec a;
     a.acq = acq;
@@ -718,28 +734,54 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
     a.p1 = (params && acq != ACQ_UCB && acq >= 0) ? params[1] : 0.0;
     a.mean_c = g->mean_c[bo];
     a.kss = (bo == 0) ? g->scale : -2.0 * g->s * g->s * g->scale * phi_prime0(g->kind);
-    for (int64_t c0 = 0; c0 < m; c0 += mc) {
+    const int d = g->d;
+    auto build_ks = [&](int64_t c0, int buf, cudaStream_t s_) -> int {
         const int64_t mvalid = std::min(mc, m - c0);
         const int64_t mc_eff = (mvalid + NB - 1) / NB * NB;
-        const int d = g->d;
-        if ((rc = prof_mark(c))) return rc;
-        if (d <= 4) launch_ks<4>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
-        else if (d <= 8) launch_ks<8>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
-        else if (d <= 12) launch_ks<12>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
-        else if (d <= 16) launch_ks<16>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
-        else if (d <= 20) launch_ks<20>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
-        else if (d <= 24) launch_ks<24>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
-        else if (d <= 32) launch_ks<32>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb);
+        double* Ks = KsB[buf];
+        double* pmean = pmB[buf];
+        if (d <= 4) launch_ks<4>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
+        else if (d <= 8) launch_ks<8>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
+        else if (d <= 12) launch_ks<12>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
+        else if (d <= 16) launch_ks<16>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
+        else if (d <= 20) launch_ks<20>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
+        else if (d <= 24) launch_ks<24>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
+        else if (d <= 32) launch_ks<32>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
         else
-            ks_build_generic_kernel<<<dim3(npb, (unsigned)(mc_eff / KS_CB)), 128, 0, st>>>(
+            ks_build_generic_kernel<<<dim3(npb, (unsigned)(mc_eff / KS_CB)), 128, 0, s_>>>(
                 gp_spec(g), g->dXsT, g->ldx, g->n, g->N, Npad, g->dAlpha, dXc, c0, m, bo, Ks, pmean, mc);
         KL(c);
-        if ((rc = prof_mark(c))) return rc;
+        return ABO_OK;
+    };
+    cudaStream_t st2 = c->stream2;
+    if (overlap) {
+        CU(cudaEventRecord(c->ev_a, st));                 // the builder stream must see the candidates / posterior
+        CU(cudaStreamWaitEvent(st2, c->ev_a, 0));
+        if ((rc = build_ks(0, 0, st2))) return rc;
+        CU(cudaEventRecord(c->ev_ks[0], st2));
+    }
+    int64_t ci = 0;
+    for (int64_t c0 = 0; c0 < m; c0 += mc, ++ci) {
+        const int64_t mvalid = std::min(mc, m - c0);
+        const int64_t mc_eff = (mvalid + NB - 1) / NB * NB;
+        const int buf = overlap ? (int)(ci & 1) : 0;
+        if (overlap) {
+            CU(cudaStreamWaitEvent(st, c->ev_ks[buf], 0));
+            if (c0 + mc < m) {                            // next chunk's K* into the other buffer
+                if (ci >= 1) CU(cudaStreamWaitEvent(st2, c->ev_sw[buf ^ 1], 0));   // its last reader is done
+                if ((rc = build_ks(c0 + mc, buf ^ 1, st2))) return rc;
+                CU(cudaEventRecord(c->ev_ks[buf ^ 1], st2));
+            }
+        } else {
+            if ((rc = prof_mark(c))) return rc;
+            if ((rc = build_ks(c0, 0, st))) return rc;
+            if ((rc = prof_mark(c))) return rc;
+        }
         if ((rc = prof_mark(c))) return rc;
         if (use_v1) {
             GemmParams p{};
             p.A = g->dLinv; p.lda = g->ld;
-            p.B = Ks; p.ldb = Npad;
+            p.B = KsB[buf]; p.ldb = Npad;
             p.M = (int)Npad; p.N = (int)mc_eff; p.K = (int)Npad;
             p.flags = KHI_M | REV_M;
             p.sumsq = sumsq; p.sumsq_ld = mc;
@@ -748,16 +790,17 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
             SweepParams sp;
             sp.T = T; sp.ncb = (int)(mc_eff / NB); sp.sumsq = sumsq; sp.sumsq_ld = mc;
             const int grid = std::min(c->sms, sp.T * sp.ncb);
-            sweep_tma_kernel<<<grid, SW_THREADS, SW_SMEM_BYTES, st>>>(tmA, tmB, sp);
+            sweep_tma_kernel<<<grid, SW_THREADS, SW_SMEM_BYTES, st>>>(tmA, tmB[buf], sp);
         }
         KL(c);
         if ((rc = prof_mark(c))) return rc;
         if ((rc = prof_mark(c))) return rc;
         acq_epilogue_kernel<<<(unsigned)((mvalid + 255) / 256), 256, 0, st>>>(
-            a, pmean, npb, sumsq, T, mc, mvalid, d_mean ? d_mean + c0 : nullptr, d_var ? d_var + c0 : nullptr,
+            a, pmB[buf], npb, sumsq, T, mc, mvalid, d_mean ? d_mean + c0 : nullptr, d_var ? d_var + c0 : nullptr,
             d_score ? d_score + c0 : nullptr);
         KL(c);
         if ((rc = prof_mark(c))) return rc;
+        if (overlap) CU(cudaEventRecord(c->ev_sw[buf], st));
         if (c->profile && c->prof_used >= 6 * 512) {       // bound the event pool
             CU(cudaStreamSynchronize(st));
             if ((rc = prof_collect(c))) return rc;

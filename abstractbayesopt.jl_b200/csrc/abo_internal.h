@@ -40,6 +40,7 @@ struct abo_ctx {
     int sms = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_ks[2] = {nullptr, nullptr}, ev_sw[2] = {nullptr, nullptr};   // K* builder / contraction ping-pong
     WsBuf ws[WS_COUNT];
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
