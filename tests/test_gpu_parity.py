@@ -320,3 +320,75 @@ def test_bo_loop_branin(abo, orc):
     assert len(bo.xs) == 10 + 9 and len(acq_list) == 9          # max_iter + 1 passes (bayesian_opt.jl:163-165)
     assert min(float(v) for v in bo.ys_non_std) <= min(y0) + 1e-12
     assert all(a >= 0 for a in acq_list)
+
+
+# ---- BASELINE.json configurations at FULL size: a seeded sample of the sweep against the oracle
+#      plus size-independent properties (top-k consistency, determinism, shard independence) ----
+def _sample_check(abo, orc, gp, post, Xc, acq, acq_id, scale, nsample=3000, seed=0):
+    rng = np.random.default_rng(seed)
+    scores, ti, tv = acq.topk(gp, Xc, 100)
+    sel = np.unique(np.concatenate([rng.integers(0, len(Xc), nsample), ti]))
+    mu_o, var_o = orc.posterior_mean_var(post, Xc[sel])
+    ref = orc.acquisition(acq_id, acq.params(), mu_o, var_o)
+    mu = abo.posterior_mean(gp, Xc[sel]); var = abo.posterior_var(gp, Xc[sel])
+    cond = np.linalg.cond(post.U) ** 2
+    tol = max(RTOL, 50 * cond * 2.2e-16)
+    assert close(mu, mu_o, max(scale, np.max(np.abs(mu_o))), tol), (np.max(np.abs(mu - mu_o)), cond)
+    assert close(var, var_o, scale, tol), (np.max(np.abs(var - var_o)), cond)
+    assert close(scores[sel], ref, np.max(np.abs(ref)), 10 * tol)
+    # properties on the full set
+    assert np.all(np.isfinite(scores))
+    assert list(ti) == list(orc.sortperm_rev(scores, 100))                  # stable descending top-k
+    assert np.array_equal(tv, scores[ti])
+    # the oracle, evaluated on the GPU's top-100 plus the sample, picks the same arg-max
+    assert sel[int(orc.sortperm_rev(ref, 1)[0])] == ti[0]
+    # the same sweep in two shards gives the same scores (chunking / sharding independence)
+    half = len(Xc) // 2 + 77
+    s1 = acq(gp, Xc[:half]); s2 = acq(gp, Xc[half:])
+    assert np.array_equal(np.concatenate([s1, s2]), scores)
+    return scores
+
+
+def test_config_c2_full_size(abo, orc):
+    c = orc.make_config("C2")                                              # n = 2048, d = 6, m = 1,048,576, Matern-5/2, EI
+    gp = abo.update(abo.StandardGP(make_kernel(abo, c["kind"], c["inv_ls"], c["scale"]), c["noise"]), c["X"], c["y"])
+    post = orc.fit_standard(c["X"], c["y"], c["kind"], c["inv_ls"], c["scale"], c["noise"])
+    acq = abo.ExpectedImprovement(*c["acq_params"])
+    s = _sample_check(abo, orc, gp, post, c["Xc"], acq, 0, c["scale"])
+    # EI >= 0 (test/test_acquisition.jl:36-42) up to the cancellation of delta*Phi(z) + sigma*phi(z) once
+    # Phi(z) is a subnormal (z < -37): the same formula gives the same few-ulp-of-subnormal noise in Julia
+    assert np.all(s >= -1e-280), s.min()
+
+
+def test_config_c3_full_size(abo, orc):
+    c = orc.make_config("C3")                                              # GradientGP n = 512, d = 10 -> N = 5632
+    gp = abo.update(abo.GradientGP(make_kernel(abo, c["kind"], c["inv_ls"], c["scale"]), 11, c["noise"]), c["X"], c["Y"])
+    post = orc.fit_gradient(c["X"], c["Y"], c["kind"], c["inv_ls"], c["scale"], c["noise"])
+    acq = abo.ExpectedImprovement(*c["acq_params"])
+    _sample_check(abo, orc, gp, post, c["Xc"], acq, 0, c["scale"], nsample=1500)
+
+
+def test_config_c4_full_n(abo, orc):
+    c = orc.make_config("C4", m=200_000)                                   # n = 8192, d = 20, UCB; one shard-sized slice
+    gp = abo.update(abo.StandardGP(make_kernel(abo, c["kind"], c["inv_ls"], c["scale"]), c["noise"]), c["X"], c["y"])
+    post = orc.fit_standard(c["X"], c["y"], c["kind"], c["inv_ls"], c["scale"], c["noise"])
+    acq = abo.UpperConfidenceBound(2.0)
+    _sample_check(abo, orc, gp, post, c["Xc"], acq, 2, c["scale"], nsample=1500)
+    L = gp.gpx.factor(0)
+    assert np.max(np.abs(L - post.U.T)) < 1e-9
+
+
+def test_config_c5_full_size(abo, orc):
+    c = orc.make_config("C5")                                              # 256 restarts, n = 1024, d = 8
+    gp = abo.StandardGP(abo.SqExponentialKernel(), c["noise"])
+    val, grad, info = abo.nlml_batch(gp, c["theta"], c["X"], c["y"])
+    ok = info == 0
+    assert ok.sum() >= 200 and np.all(np.isfinite(val[ok])) and np.all(np.isinf(val[~ok]))
+    for r in np.flatnonzero(ok)[::37]:
+        v_o, g_o = orc.nlml(c["X"], c["y"], 0, c["theta"][r, 0], c["theta"][r, 1], c["noise"], want_grad=True)
+        assert abs(val[r] - v_o) <= 1e-8 * abs(v_o), (r, val[r], v_o)
+        assert np.all(np.abs(grad[r] - g_o) <= 1e-6 * np.maximum(np.abs(g_o), 1.0)), (r, grad[r], g_o)
+    # batching independence: a restart evaluated alone gives the same bits
+    r = int(np.flatnonzero(ok)[5])
+    v1, g1, _ = abo.nlml_batch(gp, c["theta"][r:r + 1], c["X"], c["y"])
+    assert v1[0] == val[r] and np.array_equal(g1[0], grad[r])
