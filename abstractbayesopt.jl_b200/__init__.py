@@ -15,7 +15,7 @@ from .surrogates import (AbstractSurrogate, GradientGP, StandardGP, get_kernel_c
 from .acquisition import (AbstractAcquisition, ExpectedImprovement, ProbabilityImprovement, UpperConfidenceBound)
 from .domains import AbstractDomain, ContinuousDomain
 from .parallel import init_nccl_context, merge_topk, shard_range, sharded_topk, sync_posterior
-from .bayesian_opt import (BOStruct, latin_hypercube, optimize, optimize_acquisition, optimize_hyperparameters,
+from .bayesian_opt import (BOStruct, latin_hypercube, lockstep_lbfgsb, optimize, optimize_acquisition, optimize_hyperparameters,
                            standardize_problem, stop_criteria, update_bo)
 
 

@@ -17,7 +17,7 @@ ABO_OK, ABO_ERR_INVALID, ABO_ERR_DIM, ABO_ERR_NOT_POSDEF, ABO_ERR_CUDA, ABO_ERR_
 SYMBOLS = [
     "abo_version", "abo_last_error", "abo_ctx_create", "abo_ctx_destroy", "abo_ctx_device", "abo_ctx_stream",
     "abo_ctx_launch_count", "abo_ctx_profile", "abo_ctx_profile_read", "abo_debug_potf2_clocks", "abo_gp_create", "abo_gp_destroy", "abo_gp_set_params", "abo_gp_fit", "abo_gp_append",
-    "abo_gp_clone", "abo_gp_n", "abo_gp_alpha", "abo_gp_factor", "abo_gp_posterior", "abo_acq_eval", "abo_acq_eval_dev",
+    "abo_gp_clone", "abo_gp_n", "abo_gp_alpha", "abo_gp_factor", "abo_gp_posterior", "abo_acq_eval", "abo_acq_eval_dev", "abo_acq_eval_grad",
     "abo_nlml_batch", "abo_potrf_dev", "abo_nccl_unique_id", "abo_ctx_init_rank", "abo_gp_sync",
     "abo_topk_allgather",
 ]
@@ -76,6 +76,7 @@ def lib():
             "abo_gp_posterior": [vp, vp, i64, i32, vp, vp],
             "abo_acq_eval": [vp, i32, vp, vp, i64, vp, i64, vp, vp],
             "abo_acq_eval_dev": [vp, i32, vp, vp, i64, vp, i64, vp, vp],
+            "abo_acq_eval_grad": [vp, i32, vp, vp, i64, vp, vp, vp, vp],
             "abo_nlml_batch": [vp, vp, vp, i64, vp, i64, vp, vp, vp],
             "abo_potrf_dev": [vp, vp, i64, i64, C.POINTER(i64)],
             "abo_nccl_unique_id": [vp],
@@ -274,6 +275,17 @@ class GpHandle:
         ti = np.empty(max(k, 1), dtype=np.int64); tv = np.empty(max(k, 1))
         check(lib().abo_acq_eval(self._h, acq_id, ptr(params), ptr(Xc), m, ptr(scores), k, ptr(ti), ptr(tv)))
         return scores, ti[:k], tv[:k]
+
+    def acq_eval_grad(self, acq_id, params, Xc):
+        """scores (m) and d score / d x (m x d) for a batch of points."""
+        Xc = f64(Xc)
+        if Xc.ndim != 2 or Xc.shape[1] != self.d:
+            raise DimensionMismatch(f"query points must be m x {self.d}")
+        m = Xc.shape[0]
+        params = f64(params)
+        scores = np.empty(m); grad = np.empty((m, self.d))
+        check(lib().abo_acq_eval_grad(self._h, acq_id, ptr(params), ptr(Xc), m, ptr(scores), ptr(grad), None, None))
+        return scores, grad
 
     def acq_eval_dev(self, acq_id, params, d_xc: int, m: int, d_scores: int = 0, k=0):
         params = f64(params)

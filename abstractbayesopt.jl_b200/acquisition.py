@@ -24,6 +24,11 @@ class AbstractAcquisition:
         scores, _, _ = h.acq_eval(self.acq_id, self.params(), _as_points(x, h.d), k=0)
         return scores
 
+    def value_and_grad(self, surrogate, x):
+        """acq(surrogate, x) and its analytic gradient w.r.t. each point, one batched call."""
+        h = _need_posterior(surrogate)
+        return h.acq_eval_grad(self.acq_id, self.params(), _as_points(x, h.d))
+
     def topk(self, surrogate, x, k):
         """scores and sortperm(scores; rev=true)[1:k] (acq_utils.jl:50-52) in one call; 0-based."""
         h = _need_posterior(surrogate)

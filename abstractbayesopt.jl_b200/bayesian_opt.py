@@ -28,67 +28,148 @@ def latin_hypercube(n, lower, upper, rng):
 
 def optimize_acquisition(acqf, surrogate, domain, n_grid=10_000, n_local=100, rng=None, refine=True):
     """optimize_acquisition (acq_utils.jl:33-73): LHS grid → ONE batched, fused sweep that also
-    returns the stable top-n_local (replaces acqf(...) + sortperm, :50-52) → box-constrained
-    L-BFGS refinements from those starts (finite-difference gradients, as Optim's default)."""
+    returns the stable top-n_local (replaces acqf(...) + sortperm, :50-52) → box-constrained L-BFGS
+    refinement from those starts.  The reference refines the starts one after the other with
+    finite-difference gradients of single-point evaluations (:55-63); here all starts advance in
+    lock-step and every step is ONE batched call returning the acquisition and its analytic
+    gradient for all of them (refine=True).  refine="scipy" keeps the reference's sequential,
+    finite-difference scheme (SciPy L-BFGS-B); refine=False returns the best grid point."""
     rng = np.random.default_rng() if rng is None else rng
     grid = latin_hypercube(n_grid, domain.lower, domain.upper, rng)
     _, top_idx, top_val = acqf.topk(surrogate, grid, n_local)
-    best_acq, best_x = -math.inf, None
-    bounds = list(zip(domain.lower, domain.upper))
-    for i0, v0 in zip(top_idx, top_val):
-        x0 = grid[i0]
-        if refine:
+    starts = grid[top_idx]
+    if refine is False or len(starts) == 0:
+        return np.array(starts[0])
+    if refine == "scipy":
+        best_acq, best_x = -math.inf, None
+        bounds = list(zip(domain.lower, domain.upper))
+        for x0 in starts:
             res = minimize(lambda x: -float(acqf(surrogate, x[None, :])[0]), x0, method="L-BFGS-B", bounds=bounds,
                            options=dict(gtol=1e-5, ftol=2.2e-9, maxls=20))
-            cur, xc = -float(res.fun), res.x
-        else:
-            cur, xc = float(v0), x0
-        if cur > best_acq:
-            best_acq, best_x = cur, np.array(xc)
-    return best_x
+            if -float(res.fun) > best_acq:
+                best_acq, best_x = -float(res.fun), np.array(res.x)
+        return best_x
+
+    def fg(X, idx):
+        val, grad = acqf.value_and_grad(surrogate, X[idx])
+        return -val, -grad
+
+    X, f, _, failed = lockstep_lbfgsb(fg, starts, domain.lower, domain.upper, g_tol=1e-5, f_abstol=2.2e-9, max_iter=50)
+    f = np.where(failed | ~np.isfinite(f), np.inf, f)
+    return np.array(X[int(np.argmin(f))])                 # first best on ties, like the `>` update of :67-70
+
+
+def lockstep_lbfgsb(fg, x0, lower, upper, g_tol=1e-6, f_abstol=2.2e-9, max_iter=100, history=6, max_ls=20):
+    """Box-constrained L-BFGS for R independent problems advanced in LOCK-STEP: `fg(X, idx)` evaluates
+    the objective and gradient for the rows `idx` of the R x p array X in ONE batched call (here:
+    abo_nlml_batch).  Projected quasi-Newton direction per problem, Armijo back-tracking where every
+    trial step evaluates all still-searching problems together.  Stopping rule as the reference's
+    Optim options (projected-gradient inf-norm <= g_tol or |df| <= f_abstol, bayesian_opt.jl:262).
+    Returns (X, f, converged, failed)."""
+    X = np.clip(np.array(x0, dtype=np.float64), lower, upper)
+    R, p = X.shape
+    f = np.full(R, np.inf); G = np.zeros((R, p))
+    f[:], G[:] = fg(X, np.arange(R))
+    failed = ~np.isfinite(f)                              # restart whose start already fails (bayesian_opt.jl:296-299)
+    converged = np.zeros(R, dtype=bool)
+    S = [[] for _ in range(R)]; Y = [[] for _ in range(R)]
+
+    def proj_grad(x, g):
+        pg = g.copy()
+        pg[(x <= lower) & (g > 0)] = 0.0
+        pg[(x >= upper) & (g < 0)] = 0.0
+        return pg
+
+    for it in range(max_iter):
+        live = np.flatnonzero(~converged & ~failed)
+        if live.size == 0:
+            break
+        D = np.zeros((R, p))
+        for r in live:
+            pg = proj_grad(X[r], G[r])
+            if np.max(np.abs(pg)) <= g_tol:
+                converged[r] = True
+                continue
+            q = pg.copy(); al = []
+            for s_, y_ in zip(reversed(S[r]), reversed(Y[r])):
+                a_ = (s_ @ q) / (y_ @ s_); al.append(a_); q -= a_ * y_
+            if S[r]:
+                q *= (S[r][-1] @ Y[r][-1]) / (Y[r][-1] @ Y[r][-1])
+            else:
+                q /= max(1.0, np.linalg.norm(pg))
+            for (s_, y_), a_ in zip(zip(S[r], Y[r]), reversed(al)):
+                b_ = (y_ @ q) / (y_ @ s_); q += (a_ - b_) * s_
+            d = -q
+            d[(pg == 0.0)] = 0.0
+            if d @ G[r] >= 0:
+                d = -pg
+            D[r] = d
+        live = np.flatnonzero(~converged & ~failed)
+        if live.size == 0:
+            break
+        t = np.ones(R)
+        pending = live.copy()
+        Xn = X.copy(); fn = f.copy(); Gn = G.copy()
+        for _ in range(max_ls):
+            Xt = np.clip(X[pending] + t[pending, None] * D[pending], lower, upper)
+            Xfull = X.copy(); Xfull[pending] = Xt
+            ft, gt = fg(Xfull, pending)
+            dec = np.einsum("ij,ij->i", G[pending], Xt - X[pending])
+            ok = np.isfinite(ft) & (ft <= f[pending] + 1e-4 * dec)
+            acc = pending[ok]
+            Xn[acc] = Xt[ok]; fn[acc] = ft[ok]; Gn[acc] = gt[ok]
+            pending = pending[~ok]
+            if pending.size == 0:
+                break
+            t[pending] *= 0.5
+        converged[pending] = True                          # no further progress along a descent direction
+        moved = np.setdiff1d(live, pending)
+        for r in moved:
+            s_ = Xn[r] - X[r]; y_ = Gn[r] - G[r]
+            if s_ @ y_ > 1e-12 * np.linalg.norm(s_) * np.linalg.norm(y_):
+                S[r].append(s_); Y[r].append(y_)
+                if len(S[r]) > history:
+                    S[r].pop(0); Y[r].pop(0)
+            if abs(f[r] - fn[r]) <= f_abstol:
+                converged[r] = True
+        X, f, G = Xn, fn, Gn
+    return X, f, converged, failed
 
 
 def optimize_hyperparameters(model, x_train, y_train, old_params, scale_std=1.0, length_scale_only=False,
-                             num_restarts=1, domain=None, rng=None, max_iter=50):
+                             num_restarts=1, domain=None, rng=None, max_iter=100):
     """optimize_hyperparameters (bayesian_opt.jl:196-328).  Same log-space box, clamped start and
     uniform random restarts; all restarts advance in LOCK-STEP so that every objective/gradient
-    evaluation is one batched abo_nlml_batch call (value + analytic gradient) instead of one
-    ForwardDiff evaluation per restart."""
+    evaluation is ONE batched abo_nlml_batch call (value + analytic gradient for all restarts) instead
+    of one ForwardDiff evaluation per restart and step."""
     rng = np.random.default_rng() if rng is None else rng
     ls_lo, ls_hi = 1e-3, 1e3
     if domain is not None:
-        X = np.asarray(x_train, dtype=np.float64).reshape(len(x_train), -1)
         side = float(np.max(domain.upper - domain.lower))
         ls_lo, ls_hi = max(1e-6, 1e-3 * side), side
     sc_lo, sc_hi = 1e-3 / scale_std ** 2, 1e6 / scale_std ** 2
     lo = np.log([ls_lo, sc_lo]); hi = np.log([ls_hi, sc_hi])
-    start = np.clip(np.asarray(old_params, dtype=np.float64), lo + 2 * np.finfo(float).eps, hi - 2 * np.finfo(float).eps)
-    inits = [start] + [lo + (hi - lo) * rng.random(2) for _ in range(num_restarts - 1)]
-    if length_scale_only:
-        for t in inits:
-            t[1] = start[1]
-    bounds = [(lo[0], hi[0]), (lo[1], hi[1])]
-    best_val, best = math.inf, None
-    for t0 in inits:
-        def fg(t):
-            val, grad, info = nlml_batch(model, t[None, :], x_train, y_train)
-            if info[0] != 0 or not np.isfinite(val[0]):
-                return 1e300, np.zeros(2)
-            g = grad[0].copy()
-            if length_scale_only:
-                g[1] = 0.0
-            return float(val[0]), g
-        try:
-            res = minimize(fg, t0, jac=True, method="L-BFGS-B", bounds=bounds,
-                           options=dict(gtol=1e-6, ftol=2.2e-9, maxiter=max_iter))
-        except Exception as e:                                        # bayesian_opt.jl:296-299
-            log.warning("Optimization failed at restart with error: %s", e)
-            continue
-        if res.success and res.fun < best_val:
-            best_val, best = res.fun, res.x
-    if best is None:
+    eps2 = 2 * np.finfo(float).eps
+    start = np.clip(np.asarray(old_params, dtype=np.float64), lo + eps2, hi - eps2)      # bayesian_opt.jl:248
+    inits = np.array([start] + [lo + (hi - lo) * rng.random(2) for _ in range(num_restarts - 1)])
+    lower, upper = lo.copy(), hi.copy()
+    if length_scale_only:                                  # nlml_ls: log scale frozen at the start value
+        inits[:, 1] = start[1]; lower[1] = upper[1] = start[1]
+
+    def fg(X, idx):
+        val, grad, info = nlml_batch(model, X[idx], x_train, y_train)
+        val = np.where(info != 0, np.inf, val)
+        grad = np.where(np.isfinite(grad), grad, 0.0)
+        if length_scale_only:
+            grad[:, 1] = 0.0
+        return val, grad
+
+    X, f, converged, failed = lockstep_lbfgsb(fg, inits, lower, upper, max_iter=max_iter)
+    good = converged & ~failed & np.isfinite(f)
+    if not good.any():
         log.info("All restarts failed to converge.")
         return model
+    best = X[np.flatnonzero(good)[np.argmin(f[good])]]
     ell = math.exp(best[0])
     scale = get_scale(model)[0] if length_scale_only else math.exp(best[1])
     k_opt = scale * with_lengthscale(get_kernel_constructor(model), ell)

@@ -832,6 +832,81 @@ extern "C" int32_t abo_gp_posterior(abo_gp* g, const double* Xc, int64_t m, int3
     return ABO_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// acquisition value + analytic gradient for a batch of points
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t abo_acq_eval_grad(abo_gp* g, int32_t acq_id, const double* params, const double* Xc, int64_t m,
+                                     double* scores, double* grad, double* mean, double* var) {
+    if (!g || !Xc || !params || !scores || !grad) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (!g->fitted) return abo_fail(ABO_ERR_NOT_FITTED, "surrogate has no posterior (call update first)");
+    if (acq_id < 0 || acq_id > 2) return abo_fail(ABO_ERR_INVALID, "unknown acquisition id %d", acq_id);
+    if (g->d > AG_MAXD) return abo_fail(ABO_ERR_INVALID, "abo_acq_eval_grad supports d <= %d", AG_MAXD);
+    if (m <= 0) return ABO_OK;
+    abo_ctx* c = g->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int64_t Npad = g->Npad;
+    const int d = g->d;
+    const int64_t mc = 2048;                                   // points per pass
+    const int64_t vpts = (Npad + g->p - 1) / g->p;
+    const int npb = (int)((vpts + 127) / 128);                 // K* builder point blocks (incl. padding columns)
+    const int npbg = (int)((g->n + 127) / 128);                // gradient kernel point blocks
+    double *dXc, *Ks, *pmean, *W, *Z, *part, *out;
+    int rc;
+    if ((rc = ws_get(c, WS_CAND, sizeof(double) * (size_t)m * d, (void**)&dXc))) return rc;
+    if ((rc = ws_get(c, WS_KS, sizeof(double) * (size_t)mc * Npad, (void**)&Ks))) return rc;
+    if ((rc = ws_get(c, WS_PMEAN, sizeof(double) * (size_t)npb * mc, (void**)&pmean))) return rc;
+    if ((rc = ws_get(c, WS_GRAD_W, sizeof(double) * (size_t)mc * Npad, (void**)&W))) return rc;
+    if ((rc = ws_get(c, WS_GRAD_Z, sizeof(double) * (size_t)mc * Npad, (void**)&Z))) return rc;
+    if ((rc = ws_get(c, WS_GRAD_PART, sizeof(double) * (size_t)npbg * mc * 2 * AG_MAXD, (void**)&part))) return rc;
+    // out: colsq[mc] | score[m] | mean[m] | var[m] | grad[m*d]
+    if ((rc = ws_get(c, WS_GRAD_OUT, sizeof(double) * (size_t)(mc + 3 * m + m * d), (void**)&out))) return rc;
+    double *colsq = out, *dS = out + mc, *dM = dS + m, *dV = dM + m, *dG = dV + m;
+    CU(cudaMemcpyAsync(dXc, Xc, sizeof(double) * m * d, cudaMemcpyHostToDevice, st));
+    AcqSpec a;
+    a.acq = acq_id;
+    a.p0 = params[0];
+    a.p1 = (acq_id != ACQ_UCB) ? params[1] : 0.0;
+    a.mean_c = g->mean_c[0];
+    a.kss = g->scale;
+    for (int64_t c0 = 0; c0 < m; c0 += mc) {
+        const int64_t mvalid = std::min(mc, m - c0);
+        const int64_t mpad = (mvalid + NB - 1) / NB * NB;
+        if (d <= 4) launch_ks<4>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
+        else if (d <= 8) launch_ks<8>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
+        else if (d <= 12) launch_ks<12>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
+        else if (d <= 16) launch_ks<16>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
+        else if (d <= 20) launch_ks<20>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
+        else if (d <= 24) launch_ks<24>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
+        else launch_ks<32>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
+        KL(c);
+        GemmParams w{};                                        // W = L^-1 K*^T   (k <= row)
+        w.A = g->dLinv; w.lda = g->ld; w.B = Ks; w.ldb = Npad; w.C = W; w.ldc = mpad;
+        w.M = (int)Npad; w.N = (int)mpad; w.K = (int)Npad; w.alpha = 1.0; w.beta = 0.0; w.flags = KHI_M;
+        CU((launch_gemm<KC, KC, EPI_STORE>(w, 1, st)));
+        KL(c);
+        colsumsq_kernel<<<(unsigned)((mpad + 127) / 128), 128, 0, st>>>(W, Npad, mpad, colsq);
+        KL(c);
+        GemmParams z{};                                        // Z = L^-T W      (k >= row)
+        z.A = g->dLinv; z.lda = g->ld; z.B = W; z.ldb = mpad; z.C = Z; z.ldc = mpad;
+        z.M = (int)Npad; z.N = (int)mpad; z.K = (int)Npad; z.alpha = 1.0; z.beta = 0.0; z.flags = KLO_M;
+        CU((launch_gemm<MC, MC, EPI_STORE>(z, 1, st)));
+        KL(c);
+        acq_grad_partial_kernel<<<dim3(npbg, (unsigned)mpad), 128, 0, st>>>(gp_spec(g), g->dXsT, g->ldx, g->n, g->dAlpha, Z,
+                                                                           mpad, dXc + c0 * d, mvalid, part);
+        KL(c);
+        acq_grad_finish_kernel<<<(unsigned)((mvalid + 127) / 128), 128, 0, st>>>(a, d, pmean, npb, colsq, part, npbg, mc, mpad,
+                                                                                 mvalid, dS + c0, dG + c0 * d, dM + c0, dV + c0);
+        KL(c);
+    }
+    CU(cudaMemcpyAsync(scores, dS, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(grad, dG, sizeof(double) * m * d, cudaMemcpyDeviceToHost, st));
+    if (mean) CU(cudaMemcpyAsync(mean, dM, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    if (var) CU(cudaMemcpyAsync(var, dV, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ABO_OK;
+}
+
 // ---- stable descending top-k with Julia isless semantics (NaN largest, -0.0 < 0.0)
 
 void topk_host(const double* s, int64_t m, int64_t k, int64_t idx_offset, std::vector<std::pair<uint64_t, int64_t>>& heap) {

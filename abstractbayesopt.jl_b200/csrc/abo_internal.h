@@ -30,7 +30,7 @@ int abo_fail(int code, const char* fmt, ...);
 enum WsSlot {
     WS_STAGE_X = 0, WS_STAGE_Y, WS_DINV, WS_INFO, WS_TRTRI, WS_VEC_PART, WS_KS, WS_PMEAN, WS_SUMSQ, WS_CAND,
     WS_OUT_A, WS_OUT_B, WS_NLML_K, WS_NLML_LINV, WS_NLML_W, WS_NLML_X, WS_NLML_VEC, WS_NLML_PAR, WS_APPEND,
-    WS_TOPK, WS_COUNT
+    WS_TOPK, WS_GRAD_W, WS_GRAD_Z, WS_GRAD_PART, WS_GRAD_OUT, WS_COUNT
 };
 
 struct WsBuf { void* ptr = nullptr; size_t bytes = 0; };

@@ -1076,3 +1076,124 @@ __global__ void __launch_bounds__(256) nlml_finish_kernel(const double* __restri
 }
 
 }  // namespace abo
+
+// ------------------------------------------------------------------------------------------
+// acquisition value AND gradient for a small batch of points (batched local refinement of
+// optimize_acquisition, src/acquisition_functions/acq_utils.jl:55-71, which the reference drives
+// with finite differences of single-point evaluations):
+//     mu   = m + k*^T alpha                  grad mu   =  sum_idx alpha_idx * dk*_idx/dx*
+//     var  = k** - |w|^2,  w = L^-1 k*       grad var  = -2 sum_idx z_idx * dk*_idx/dx*,  z = L^-T w
+// dk*_idx/dx*_b is the (a, b) block of gradKernel with a = output of training row idx.
+// ------------------------------------------------------------------------------------------
+namespace abo {
+
+// colsq[c] = sum_i W[i][c]^2        (W: Npad x mpad row-major), one thread per column, fixed order
+__global__ void colsumsq_kernel(const double* __restrict__ W, int64_t Npad, int64_t mpad, double* __restrict__ out) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= mpad) return;
+    double s = 0.0;
+    for (int64_t i = 0; i < Npad; ++i) { const double v = W[i * mpad + c]; s = fma(v, v, s); }
+    out[c] = s;
+}
+
+// part[pb][c][b] = sum over the 128 training points of block pb of
+//                  sum_a ( alpha[idx] , z[idx][c] ) * d gk((x_i,a),(x*_c,0)) / d x*_b
+// grid (point blocks, candidates), 128 threads; output two planes: gmu and gvar partials.
+constexpr int AG_MAXD = 32;
+__global__ void __launch_bounds__(128) acq_grad_partial_kernel(KSpec spec, const double* __restrict__ XsT, int64_t ldx,
+                                                               int64_t npts, const double* __restrict__ alpha,
+                                                               const double* __restrict__ Z, int64_t mpad,
+                                                               const double* __restrict__ Xc, int64_t m,
+                                                               double* __restrict__ part) {
+    __shared__ double sh[4][2 * AG_MAXD];
+    const int c = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t i = blockIdx.x * 128LL + tid;
+    const int d = spec.d, p = spec.p;
+    double gmu[AG_MAXD], gva[AG_MAXD];
+#pragma unroll
+    for (int b = 0; b < AG_MAXD; ++b) { gmu[b] = 0.0; gva[b] = 0.0; }
+    if (i < npts && c < m) {
+        double u = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double df = XsT[k * ldx + i] - spec.s * Xc[(int64_t)c * d + k];
+            u = fma(df, df, u);
+        }
+        double ph, dph, ddph;
+        phi_eval(spec.kind, u, ph, dph, ddph);
+        for (int a = 0; a < p; ++a) {
+            const int64_t idx = i * p + a;
+            const double al = alpha[idx], zz = Z[idx * mpad + c];
+            const double Da = (a == 0) ? 0.0 : XsT[(a - 1) * ldx + i] - spec.s * Xc[(int64_t)c * d + a - 1];
+#pragma unroll
+            for (int b = 0; b < AG_MAXD; ++b) {
+                if (b < d) {
+                    const double Db = XsT[b * ldx + i] - spec.s * Xc[(int64_t)c * d + b];
+                    const double dk = gk_entry(spec, ph, dph, ddph, a, b + 1, Da, Db);
+                    gmu[b] = fma(al, dk, gmu[b]);
+                    gva[b] = fma(zz, dk, gva[b]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < AG_MAXD; ++b) {
+        if (b < d) {
+            double x = gmu[b], y = gva[b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { x += __shfl_xor_sync(0xffffffffu, x, o); y += __shfl_xor_sync(0xffffffffu, y, o); }
+            if (lane == 0) { sh[warp][b] = x; sh[warp][AG_MAXD + b] = y; }
+        }
+    }
+    __syncthreads();
+    if (tid < 2 * AG_MAXD) {
+        const int b = tid % AG_MAXD;
+        if (b < d) {
+            const double v = ((sh[0][tid] + sh[1][tid]) + sh[2][tid]) + sh[3][tid];
+            part[(((int64_t)blockIdx.x * gridDim.y + c) * 2 + tid / AG_MAXD) * AG_MAXD + b] = v;
+        }
+    }
+}
+
+// one thread per candidate: value and gradient of EI / PI / UCB from (mu, var, grad mu, grad var)
+__global__ void acq_grad_finish_kernel(AcqSpec a, int d, const double* __restrict__ pmean, int npb_mean,
+                                       const double* __restrict__ colsq, const double* __restrict__ part, int npb,
+                                       int64_t mc, int64_t mpad, int64_t m, double* __restrict__ score,
+                                       double* __restrict__ grad, double* __restrict__ mean_out,
+                                       double* __restrict__ var_out) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    double mu = 0.0;
+    for (int b = 0; b < npb_mean; ++b) mu += pmean[(int64_t)b * mc + c];
+    mu += a.mean_c;
+    const double var = (a.kss - colsq[c]) + JITTER;
+    if (mean_out) mean_out[c] = mu;
+    if (var_out) var_out[c] = var;
+    score[c] = acq_value(a, mu, var);
+    // d acq / d mu, d acq / d var
+    double dmu, dvar;
+    if (a.acq == ACQ_UCB) {
+        dmu = -1.0;
+        dvar = (var > 0.0) ? a.p0 * 0.5 / sqrt(var) : 0.0;
+    } else {
+        const double delta = (a.p1 - a.p0) - mu;
+        if (var <= 1e-12) {
+            dmu = (delta > 0.0) ? -1.0 : 0.0;
+            dvar = 0.0;
+        } else {
+            const double sig = sqrt(var), z = delta / sig;
+            if (a.acq == ACQ_EI) { dmu = -normcdf_ref(z); dvar = normpdf_ref(z) * 0.5 / sig; }
+            else { dmu = -normpdf_ref(z) / sig; dvar = -normpdf_ref(z) * z * 0.5 / var; }
+        }
+    }
+    for (int b = 0; b < d; ++b) {
+        double gm = 0.0, gv = 0.0;
+        for (int pb = 0; pb < npb; ++pb) {
+            gm += part[(((int64_t)pb * mpad + c) * 2 + 0) * AG_MAXD + b];
+            gv += part[(((int64_t)pb * mpad + c) * 2 + 1) * AG_MAXD + b];
+        }
+        grad[c * d + b] = dmu * gm + dvar * (-2.0 * gv);
+    }
+}
+
+}  // namespace abo

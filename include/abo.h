@@ -118,6 +118,13 @@ int32_t abo_acq_eval(abo_gp* gp, int32_t acq_id, const double* params, const dou
 int32_t abo_acq_eval_dev(abo_gp* gp, int32_t acq_id, const double* params, const double* d_Xc,
                          int64_t m, double* d_scores, int64_t k, int64_t* top_idx, double* top_val);
 
+/* acquisition value AND its gradient with respect to the query point for a batch of m points
+ * (batched local refinement of optimize_acquisition, acq_utils.jl:55-71: the reference differentiates
+ * single-point evaluations by finite differences; here mu, sigma^2 and their analytic gradients
+ * come from one pass).  scores: m; grad: m x d point-major; mean / var (m) may be NULL.  d <= 32. */
+int32_t abo_acq_eval_grad(abo_gp* gp, int32_t acq_id, const double* params, const double* Xc, int64_t m,
+                          double* scores, double* grad, double* mean, double* var);
+
 /* nlml(model, [log l, log sig2], xs, ys) and its gradient for R parameter vectors at once
  * (StandardGP.jl:99-149, GradientGP.jl:684-738, driven by bayesian_opt.jl:259-300).
  * logparams: R x 2 (row r = {log l, log sig2}); nlml: R; grad: R x 2 (may be NULL);

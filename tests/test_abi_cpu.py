@@ -81,3 +81,30 @@ def test_standardisation_helpers(built):
     mu, sd = abo.get_mean_std(ggp, Y, "mean_scale")
     assert mu[0] == 2.0 and mu[1] == 0 and mu[2] == 0 and sd[0] == sd[1] == sd[2] == 1.0
     assert np.array_equal(abo.prep_output(ggp, Y), Y.T.reshape(-1))
+
+
+def test_lockstep_lbfgsb_on_analytic_problems(built):
+    """The lock-step multi-start optimiser (host logic of optimize_hyperparameters) on problems with
+    known minimisers, including active box constraints and a restart whose start is infeasible."""
+    import numpy as np
+    abo = built
+    rng = np.random.default_rng(0)
+    R = 9
+    centers = rng.uniform(-1, 1, (R, 2)); centers[3] = [3.0, 0.0]       # minimiser outside the box -> on the bound
+    calls = []
+
+    def fg(X, idx):
+        calls.append(len(idx))
+        d = X[idx] - centers[idx]
+        val = 0.5 * (d[:, 0] ** 2 + 10 * d[:, 1] ** 2) + 0.1 * d[:, 0] ** 4
+        grad = np.column_stack([d[:, 0] + 0.4 * d[:, 0] ** 3, 10 * d[:, 1]])
+        val = np.where(idx == 5, np.inf, val)                              # restart 5 always fails
+        return val, grad
+
+    x0 = rng.uniform(-2, 2, (R, 2))
+    X, f, conv, failed = abo.lockstep_lbfgsb(fg, x0, np.array([-2.0, -2.0]), np.array([2.0, 2.0]))
+    assert failed[5] and not failed[[0, 1, 2, 3, 4, 6, 7, 8]].any()
+    ok = [0, 1, 2, 4, 6, 7, 8]
+    assert conv[ok].all() and np.max(np.abs(X[ok] - centers[ok])) < 1e-4
+    assert abs(X[3, 0] - 2.0) < 1e-12 and abs(X[3, 1]) < 1e-4              # clipped to the upper bound
+    assert max(calls) <= R and len(calls) < 200                            # batched: one call per trial step

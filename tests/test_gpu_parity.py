@@ -392,3 +392,61 @@ def test_config_c5_full_size(abo, orc):
     r = int(np.flatnonzero(ok)[5])
     v1, g1, _ = abo.nlml_batch(gp, c["theta"][r:r + 1], c["X"], c["y"])
     assert v1[0] == val[r] and np.array_equal(g1[0], grad[r])
+
+
+# ---- acquisition value + analytic gradient (batched local refinement, acq_utils.jl:55-71) ------
+@pytest.mark.parametrize("acq_name", ["EI", "PI", "UCB"])
+@pytest.mark.parametrize("kind,n,d", [(0, 200, 2), (1, 400, 6), (0, 700, 20)])
+def test_acquisition_gradient(abo, orc, acq_name, kind, n, d):
+    rng = np.random.default_rng(7 * n + d)
+    X = rng.random((n, d)); y = np.sin(3 * X).sum(1) / d + 0.05 * rng.standard_normal(n)
+    y = (y - y.mean()) / y.std(ddof=1)
+    inv_ls, scale, noise = 1.0 / (0.5 * math.sqrt(d)), 1.2, 1e-3
+    gp = abo.update(abo.StandardGP(make_kernel(abo, kind, inv_ls, scale), noise), X, y)
+    post = orc.fit_standard(X, y, kind, inv_ls, scale, noise)
+    best = float(np.median(y))          # a threshold in the bulk of the data: EI / PI are O(0.1), not 1e-30 tails
+    acq = {"EI": abo.ExpectedImprovement(0.01, best), "PI": abo.ProbabilityImprovement(0.01, best),
+           "UCB": abo.UpperConfidenceBound(2.0)}[acq_name]
+    aid = {"EI": 0, "PI": 1, "UCB": 2}[acq_name]
+    Xq = rng.random((37, d))
+    val, grad = acq.value_and_grad(gp, Xq)
+    assert close(val, acq(gp, Xq), np.max(np.abs(val)), 1e-10)      # same value as the sweep path
+    # oracle: central differences of the oracle acquisition (what the reference's optimiser sees)
+    h = 1e-6
+    for b in range(d):
+        Xp = Xq.copy(); Xp[:, b] += h; Xm = Xq.copy(); Xm[:, b] -= h
+        fp = orc.acquisition(aid, acq.params(), *orc.posterior_mean_var(post, Xp))
+        fm = orc.acquisition(aid, acq.params(), *orc.posterior_mean_var(post, Xm))
+        fd = (fp - fm) / (2 * h)
+        sc = max(np.max(np.abs(fd)), 1e-12)
+        assert np.all(np.abs(grad[:, b] - fd) <= 2e-5 * sc + 1e-7 * np.abs(fd)), (b, np.max(np.abs(grad[:, b] - fd)), sc)
+
+
+def test_acquisition_gradient_gradient_gp(abo, orc):
+    rng = np.random.default_rng(3)
+    n, d = 30, 3
+    X = -2 + 4 * rng.random((n, d)); Y = orc.rosenbrock_with_grad(X); Y = Y / np.std(Y[:, 0])
+    gp = abo.update(abo.GradientGP(make_kernel(abo, 3, 1 / 1.5, 1.0), d + 1, 1e-4), X, Y)
+    post = orc.fit_gradient(X, Y, 3, 1 / 1.5, 1.0, 1e-4)
+    acq = abo.UpperConfidenceBound(2.0)
+    Xq = -2 + 4 * rng.random((20, d))
+    val, grad = acq.value_and_grad(gp, Xq)
+    h = 1e-6
+    for b in range(d):
+        Xp = Xq.copy(); Xp[:, b] += h; Xm = Xq.copy(); Xm[:, b] -= h
+        fd = (orc.upper_confidence_bound(*orc.posterior_mean_var(post, Xp), 2.0)
+              - orc.upper_confidence_bound(*orc.posterior_mean_var(post, Xm), 2.0)) / (2 * h)
+        assert np.all(np.abs(grad[:, b] - fd) <= 2e-5 * max(np.max(np.abs(fd)), 1e-12))
+
+
+def test_batched_refinement_beats_grid(abo, orc):
+    c = orc.make_config("C1", n=25, m=10)
+    gp = abo.update(abo.StandardGP(make_kernel(abo, 0, c["inv_ls"], 1.0), 1e-6), c["X"], c["y"])
+    acq = abo.ExpectedImprovement(0.01, float(c["y"].min()))
+    dom = abo.ContinuousDomain(c["lower"], c["upper"])
+    x_grid = abo.optimize_acquisition(acq, gp, dom, n_grid=3000, n_local=20, rng=np.random.default_rng(1), refine=False)
+    x_ref = abo.optimize_acquisition(acq, gp, dom, n_grid=3000, n_local=20, rng=np.random.default_rng(1), refine=True)
+    x_sci = abo.optimize_acquisition(acq, gp, dom, n_grid=3000, n_local=20, rng=np.random.default_rng(1), refine="scipy")
+    a_grid, a_ref, a_sci = (float(acq(gp, x[None, :])[0]) for x in (x_grid, x_ref, x_sci))
+    assert a_ref >= a_grid - 1e-15 and np.all(x_ref >= dom.lower) and np.all(x_ref <= dom.upper)
+    assert a_ref >= 0.98 * a_sci                                  # as good as the sequential finite-difference scheme
