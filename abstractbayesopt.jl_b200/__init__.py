@@ -9,10 +9,11 @@ from .kernels import (ADMatern52Kernel, ADMatern72Kernel, ApproxMatern52Kernel, 
                       extract_scale_and_lengthscale)
 from .surrogates import (AbstractSurrogate, GradientGP, StandardGP, get_kernel_constructor, get_lengthscale,
                          get_mean_std, get_scale, nlml, nlml_batch, nlml_ls, posterior_grad_mean,
-                         posterior_grad_var, posterior_mean, posterior_var, prep_input, prep_output, rescale_model,
+                         posterior_grad_var, posterior_grad_cov, posterior_cov, posterior_mean, posterior_var, prep_input, prep_output, rescale_model,
                          std_y, unstandardized_mean_and_var, update_surrogate, empty_posterior_like, _get_minimum,
                          _update_model_parameters)
-from .acquisition import (AbstractAcquisition, ExpectedImprovement, ProbabilityImprovement, UpperConfidenceBound)
+from .acquisition import (AbstractAcquisition, EnsembleAcquisition, ExpectedImprovement, GradientNormUCB,
+                          ProbabilityImprovement, UpperConfidenceBound)
 from .domains import AbstractDomain, ContinuousDomain
 from .parallel import init_nccl_context, merge_topk, shard_range, sharded_topk, sync_posterior
 from .bayesian_opt import (BOStruct, latin_hypercube, lockstep_lbfgsb, optimize, optimize_acquisition, optimize_hyperparameters,

@@ -17,7 +17,7 @@ ABO_OK, ABO_ERR_INVALID, ABO_ERR_DIM, ABO_ERR_NOT_POSDEF, ABO_ERR_CUDA, ABO_ERR_
 SYMBOLS = [
     "abo_version", "abo_last_error", "abo_ctx_create", "abo_ctx_destroy", "abo_ctx_device", "abo_ctx_stream",
     "abo_ctx_launch_count", "abo_ctx_profile", "abo_ctx_profile_read", "abo_debug_potf2_clocks", "abo_gp_create", "abo_gp_destroy", "abo_gp_set_params", "abo_gp_fit", "abo_gp_append",
-    "abo_gp_clone", "abo_gp_n", "abo_gp_alpha", "abo_gp_factor", "abo_gp_posterior", "abo_acq_eval", "abo_acq_eval_dev", "abo_acq_eval_grad",
+    "abo_gp_clone", "abo_gp_n", "abo_gp_alpha", "abo_gp_factor", "abo_gp_posterior", "abo_gp_posterior_cov", "abo_acq_eval", "abo_acq_eval_dev", "abo_acq_eval_grad",
     "abo_nlml_batch", "abo_potrf_dev", "abo_nccl_unique_id", "abo_ctx_init_rank", "abo_gp_sync",
     "abo_topk_allgather",
 ]
@@ -74,6 +74,7 @@ def lib():
             "abo_gp_alpha": [vp, vp],
             "abo_gp_factor": [vp, i32, vp],
             "abo_gp_posterior": [vp, vp, i64, i32, vp, vp],
+            "abo_gp_posterior_cov": [vp, vp, i64, i32, vp],
             "abo_acq_eval": [vp, i32, vp, vp, i64, vp, i64, vp, vp],
             "abo_acq_eval_dev": [vp, i32, vp, vp, i64, vp, i64, vp, vp],
             "abo_acq_eval_grad": [vp, i32, vp, vp, i64, vp, vp, vp, vp],
@@ -263,6 +264,15 @@ class GpHandle:
         var = np.empty(m * outputs) if want_var else None
         check(lib().abo_gp_posterior(self._h, ptr(Xc), m, outputs, ptr(mean), ptr(var)))
         return mean, var
+
+    def posterior_cov(self, Xc, outputs=1):
+        Xc = f64(Xc)
+        if Xc.ndim != 2 or Xc.shape[1] != self.d:
+            raise DimensionMismatch(f"query points must be m x {self.d}")
+        M = Xc.shape[0] * outputs
+        cov = np.empty((M, M))
+        check(lib().abo_gp_posterior_cov(self._h, ptr(Xc), Xc.shape[0], outputs, ptr(cov)))
+        return cov
 
     def acq_eval(self, acq_id, params, Xc, k=0, want_scores=True):
         Xc = f64(Xc)

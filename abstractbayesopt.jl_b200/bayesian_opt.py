@@ -40,6 +40,8 @@ def optimize_acquisition(acqf, surrogate, domain, n_grid=10_000, n_local=100, rn
     starts = grid[top_idx]
     if refine is False or len(starts) == 0:
         return np.array(starts[0])
+    if refine is True and getattr(acqf, "acq_id", -1) < 0:
+        refine = "scipy"                                # no fused value+gradient path (GradientNormUCB, ensembles)
     if refine == "scipy":
         best_acq, best_x = -math.inf, None
         bounds = list(zip(domain.lower, domain.upper))

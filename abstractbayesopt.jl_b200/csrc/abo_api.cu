@@ -250,7 +250,7 @@ int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strid
     for (int jb = 0; jb < T; ++jb) {
         double* Ajj = A + (int64_t)jb * NB * (ld + 1);
         double* Dj = Dinv + (int64_t)jb * NB * NB;
-        potf2_inv_kernel<<<batch, POTF2_THREADS, POTF2_SMEM_BYTES, st>>>(Ajj, ld, strideA, Dj, strideD, info, jb * NB);
+        potf2_ws_kernel<<<batch, 512, PW_SMEM_BYTES, st>>>(Ajj, ld, strideA, Dj, strideD, info, jb * NB);
         KL(c);
         const int rem = (int)(Npad - (int64_t)(jb + 1) * NB);
         if (rem <= 0) break;
@@ -260,14 +260,14 @@ int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strid
         g.B = Dj; g.ldb = NB; g.strideB = strideD;
         g.C = P; g.ldc = ld; g.strideC = strideA;
         g.M = rem; g.N = NB; g.K = NB; g.alpha = 1.0; g.beta = 0.0; g.flags = 0;
-        CU((launch_gemm<KC, KC, EPI_STORE>(g, batch, st)));   // L_ij = A_ij * inv(L_jj)^T
+        CU((launch_gemm_small<64, 8>(g, batch, st)));        // L_ij = A_ij * inv(L_jj)^T
         KL(c);
         GemmParams s{};
         s.A = P; s.lda = ld; s.strideA = strideA;
         s.B = P; s.ldb = ld; s.strideB = strideA;
         s.C = Ajj + (int64_t)NB * (ld + 1); s.ldc = ld; s.strideC = strideA;
         s.M = rem; s.N = rem; s.K = NB; s.alpha = -1.0; s.beta = 1.0; s.flags = LOWER_ONLY;
-        CU((launch_gemm<KC, KC, EPI_STORE>(s, batch, st)));   // A_22 -= L_21 L_21^T
+        CU((launch_gemm_small<64, 8>(s, batch, st)));        // A_22 -= L_21 L_21^T
         KL(c);
     }
     return ABO_OK;
@@ -903,6 +903,62 @@ extern "C" int32_t abo_acq_eval_grad(abo_gp* g, int32_t acq_id, const double* pa
     CU(cudaMemcpyAsync(grad, dG, sizeof(double) * m * d, cudaMemcpyDeviceToHost, st));
     if (mean) CU(cudaMemcpyAsync(mean, dM, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
     if (var) CU(cudaMemcpyAsync(var, dV, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_gp_posterior_cov(abo_gp* g, const double* Xc, int64_t m, int32_t outputs, double* cov) {
+    if (!g || !Xc || !cov) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (!g->fitted) return abo_fail(ABO_ERR_NOT_FITTED, "surrogate has no posterior (call update first)");
+    if (outputs != 1 && outputs != g->p) return abo_fail(ABO_ERR_INVALID, "outputs must be 1 or p");
+    if (m <= 0) return ABO_OK;
+    const int64_t mp = (m + KS_CB - 1) / KS_CB * KS_CB;           // rows per output block (builder granularity)
+    const int64_t Mtot = mp * outputs, Mpad = (Mtot + NB - 1) / NB * NB;
+    if (m * outputs > 8192) return abo_fail(ABO_ERR_INVALID, "posterior covariance is limited to m*outputs <= 8192");
+    abo_ctx* c = g->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int64_t Npad = g->Npad;
+    const int d = g->d;
+    const int64_t vpts = (Npad + g->p - 1) / g->p;
+    const int npb = (int)((vpts + 127) / 128);
+    double *dXc, *Ks, *pmean, *W, *G, *dcov;
+    int rc;
+    if ((rc = ws_get(c, WS_CAND, sizeof(double) * (size_t)m * d, (void**)&dXc))) return rc;
+    if ((rc = ws_get(c, WS_KS, sizeof(double) * (size_t)Mpad * Npad, (void**)&Ks))) return rc;
+    if ((rc = ws_get(c, WS_PMEAN, sizeof(double) * (size_t)npb * Mpad, (void**)&pmean))) return rc;
+    if ((rc = ws_get(c, WS_GRAD_W, sizeof(double) * (size_t)Mpad * Npad, (void**)&W))) return rc;
+    if ((rc = ws_get(c, WS_GRAD_Z, sizeof(double) * (size_t)Mpad * Mpad, (void**)&G))) return rc;
+    if ((rc = ws_get(c, WS_GRAD_OUT, sizeof(double) * (size_t)(m * outputs) * (m * outputs), (void**)&dcov))) return rc;
+    CU(cudaMemcpyAsync(dXc, Xc, sizeof(double) * m * d, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(Ks, 0, sizeof(double) * (size_t)Mpad * Npad, st));
+    for (int bo = 0; bo < outputs; ++bo) {
+        double* Kb = Ks + (size_t)bo * mp * Npad;
+        double* pm = pmean + (size_t)bo * mp;                      // (unused partial means)
+        if (d <= 4) launch_ks<4>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
+        else if (d <= 8) launch_ks<8>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
+        else if (d <= 12) launch_ks<12>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
+        else if (d <= 16) launch_ks<16>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
+        else if (d <= 20) launch_ks<20>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
+        else if (d <= 24) launch_ks<24>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
+        else if (d <= 32) launch_ks<32>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
+        else return abo_fail(ABO_ERR_INVALID, "posterior covariance supports d <= 32");
+        KL(c);
+    }
+    GemmParams w{};                                                // W = L^-1 K*^T
+    w.A = g->dLinv; w.lda = g->ld; w.B = Ks; w.ldb = Npad; w.C = W; w.ldc = Mpad;
+    w.M = (int)Npad; w.N = (int)Mpad; w.K = (int)Npad; w.alpha = 1.0; w.beta = 0.0; w.flags = KHI_M;
+    CU((launch_gemm<KC, KC, EPI_STORE>(w, 1, st)));
+    KL(c);
+    GemmParams q{};                                                // G = W^T W
+    q.A = W; q.lda = Mpad; q.B = W; q.ldb = Mpad; q.C = G; q.ldc = Mpad;
+    q.M = (int)Mpad; q.N = (int)Mpad; q.K = (int)Npad; q.alpha = 1.0; q.beta = 0.0; q.flags = 0;
+    CU((launch_gemm<MC, MC, EPI_STORE>(q, 1, st)));
+    KL(c);
+    const int64_t Mo = m * outputs;
+    cov_finish_kernel<<<(unsigned)((Mo * Mo + 255) / 256), 256, 0, st>>>(gp_spec(g), dXc, m, outputs, mp, G, Mpad, dcov);
+    KL(c);
+    CU(cudaMemcpyAsync(cov, dcov, sizeof(double) * Mo * Mo, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return ABO_OK;
 }

@@ -196,10 +196,8 @@ extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, i
             int64_t tot = ldx * d;
             scale_transpose_batched_kernel<<<dim3((unsigned)((tot + 255) / 256), nb), 256, 0, st>>>(dXraw, Xb, n, d, ldx, sb);
             KL(c);
-            for (int b = 0; b < nb; ++b) {
-                delta_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(dYraw, dYraw + N, n, p, delta + (int64_t)b * Npad);
-                KL(c);
-            }
+            delta_batched_kernel<<<dim3((unsigned)((N + 255) / 256), nb), 256, 0, st>>>(dYraw, dYraw + N, n, p, delta, Npad);
+            KL(c);
         }
         KmatBatch bt{sb, scb, ldx * d, Npad * Npad};
         kmat_kernel<<<dim3(T, T, nb), 256, 0, st>>>(spec, Xb, ldx, N, Kb, Npad, bt);

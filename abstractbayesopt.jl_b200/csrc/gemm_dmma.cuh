@@ -304,6 +304,14 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 2) gemm_small_kernel(Ge
     }
 }
 
+template <int BMT, int NW>
+inline cudaError_t launch_gemm_small(const GemmParams& p, int batch, cudaStream_t st) {
+    if (p.M <= 0 || p.N <= 0 || batch <= 0) return cudaSuccess;
+    dim3 grid(p.N / BN, p.M / BMT, batch);
+    gemm_small_kernel<BMT, NW><<<grid, NW * 32, GemmS<BMT, NW>::SMEM_BYTES, st>>>(p);
+    return cudaGetLastError();
+}
+
 template <int LA, int LB, int EPI>
 inline cudaError_t configure_gemm() {   // per device: opt in to > 48 KB dynamic shared memory
     return cudaFuncSetAttribute(gemm_dmma_kernel<LA, LB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,

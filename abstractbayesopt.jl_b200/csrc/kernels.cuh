@@ -868,6 +868,15 @@ __global__ void delta_kernel(const double* __restrict__ y, const double* __restr
     const int a = (int)(t % p);
     delta[t] = y[(int64_t)a * n + i] - mean_c[a];
 }
+// batched: the same delta replicated for every restart of the batch (blockIdx.y)
+__global__ void delta_batched_kernel(const double* __restrict__ y, const double* __restrict__ mean_c, int64_t n, int p,
+                                     double* __restrict__ delta, int64_t stride) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * p) return;
+    const int64_t i = t / p;
+    const int a = (int)(t % p);
+    delta[(int64_t)blockIdx.y * stride + t] = y[(int64_t)a * n + i] - mean_c[a];
+}
 // out-major <- point-major permutation of a length n*p vector
 __global__ void to_out_major_kernel(const double* __restrict__ v, int64_t n, int p, double* __restrict__ out) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1196,4 +1205,31 @@ __global__ void acq_grad_finish_kernel(AcqSpec a, int d, const double* __restric
     }
 }
 
+}  // namespace abo
+
+// posterior covariance over all (point, output) pairs of a small query set, out-major
+// (posterior_grad_cov, src/surrogates/GradientGP.jl:968-971):
+//   cov[(b,c),(b',c')] = gk((x_c,b),(x_c',b')) - G[b*mp + c][b'*mp + c'] + 1e-18 * delta
+// with G = W^T W, W = L^-1 K*; one thread per output entry.
+namespace abo {
+__global__ void cov_finish_kernel(KSpec spec, const double* __restrict__ Xc, int64_t m, int nout, int64_t mp,
+                                  const double* __restrict__ G, int64_t ldg, double* __restrict__ cov) {
+    const int64_t M = m * nout;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= M * M) return;
+    const int64_t r = t / M, q = t % M;
+    const int b = (int)(r / m), b2 = (int)(q / m);
+    const int64_t c = r % m, c2 = q % m;
+    double u = 0.0, Da = 0.0, Db = 0.0;
+    for (int k = 0; k < spec.d; ++k) {
+        const double df = spec.s * Xc[c * spec.d + k] - spec.s * Xc[c2 * spec.d + k];
+        u = fma(df, df, u);
+        if (k == b - 1) Da = df;
+        if (k == b2 - 1) Db = df;
+    }
+    double p, dp, ddp;
+    phi_eval(spec.kind, u, p, dp, ddp);
+    const double prior = gk_entry(spec, p, dp, ddp, b, b2, Da, Db);
+    cov[t] = (prior - G[((int64_t)b * mp + c) * ldg + (int64_t)b2 * mp + c2]) + (r == q ? JITTER : 0.0);
+}
 }  // namespace abo

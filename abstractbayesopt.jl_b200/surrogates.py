@@ -196,6 +196,18 @@ def posterior_grad_var(model, x):
     return h.posterior(_as_points(x, h.d), model.p, False, True)[1]
 
 
+def posterior_grad_cov(model, x):
+    """GradientGP.jl:968-971 — full covariance over (point, output) pairs, out-major."""
+    h = _need_posterior(model)
+    return h.posterior_cov(_as_points(x, h.d), model.p)
+
+
+def posterior_cov(model, x):
+    """cov(model.gpx(x)) for the value output."""
+    h = _need_posterior(model)
+    return h.posterior_cov(_as_points(x, h.d), 1)
+
+
 def unstandardized_mean_and_var(model, xs, params):
     """StandardGP.jl:395-404 / GradientGP.jl:1019-1030."""
     h = _need_posterior(model)

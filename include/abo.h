@@ -108,6 +108,11 @@ int32_t abo_gp_factor(const abo_gp* gp, int32_t which, double* out);
 int32_t abo_gp_posterior(abo_gp* gp, const double* Xc, int64_t m, int32_t outputs,
                          double* mean, double* var);
 
+/* full posterior covariance over all (point, output) pairs of a SMALL query set, out-major,
+ * (m*outputs)^2 doubles row-major: cov(model.gpx(x)) / posterior_grad_cov (GradientGP.jl:968-971).
+ * outputs == 1 or p; m*outputs <= 8192. */
+int32_t abo_gp_posterior_cov(abo_gp* gp, const double* Xc, int64_t m, int32_t outputs, double* cov);
+
 /* fused acquisition sweep: scores = acq(surrogate, Xc) (ExpectedImprovement.jl:40-45 etc.) and
  * sortperm(scores; rev=true)[1:k] (acq_utils.jl:50-52): stable, descending, NaN first.
  * scores (m) may be NULL; k may be 0 (top_idx/top_val then unused). */

@@ -377,6 +377,20 @@ def upper_confidence_bound(mu, var, beta):
     return -np.asarray(mu) + beta * np.sqrt(np.maximum(np.asarray(var), 0.0))
 
 
+def grad_norm_ucb(post: Posterior, Xc, beta):
+    """src/acquisition_functions/gradNormUCB.jl:43-51, point by point."""
+    Xc = np.atleast_2d(np.asarray(Xc, dtype=np.float64))
+    out = np.empty(len(Xc))
+    for c, x in enumerate(Xc):
+        mean, _ = posterior_mean_var(post, x[None, :], outputs=range(post.p))
+        S = posterior_cov(post, x[None, :])[1:, 1:]
+        m = mean[1:]
+        mu_sq = m @ m + np.trace(S)
+        var_sq = 4 * m @ (S @ m) + 2 * np.sum(S ** 2)
+        out[c] = -mu_sq + beta * math.sqrt(max(var_sq, 1e-12))
+    return out
+
+
 def acquisition(acq_id, params, mu, var):
     if acq_id == EI:
         return expected_improvement(mu, var, params[0], params[1])

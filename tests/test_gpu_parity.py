@@ -450,3 +450,51 @@ def test_batched_refinement_beats_grid(abo, orc):
     a_grid, a_ref, a_sci = (float(acq(gp, x[None, :])[0]) for x in (x_grid, x_ref, x_sci))
     assert a_ref >= a_grid - 1e-15 and np.all(x_ref >= dom.lower) and np.all(x_ref <= dom.upper)
     assert a_ref >= 0.98 * a_sci                                  # as good as the sequential finite-difference scheme
+
+
+# ---- posterior_grad_cov (GradientGP.jl:968-971; reference test test_surrogates.jl:331-351) ----
+def test_posterior_grad_cov(abo, orc):
+    xs = np.array([[0.0, 0.0], [0.5, 0.5], [1.0, 1.0]])
+    ys = np.array([[1.0, 0.1, 0.1], [0.5, 0.0, 0.0], [0.0, -0.1, -0.1]])
+    gp = abo.update(abo.GradientGP(abo.SqExponentialKernel(), 3, 0.1), xs, ys)
+    post = orc.fit_gradient(xs, ys, 0, 1.0, 1.0, 0.1)
+    cov = abo.posterior_grad_cov(gp, [[0.25, 0.25]])
+    assert cov.shape == (3, 3) and np.max(np.abs(cov - orc.posterior_cov(post, [[0.25, 0.25]]))) < 1e-10
+    rng = np.random.default_rng(2)
+    X = -2 + 4 * rng.random((40, 4)); Y = orc.rosenbrock_with_grad(X); Y = Y / np.std(Y[:, 0])
+    gp = abo.update(abo.GradientGP(make_kernel(abo, 5, 0.6, 1.5), 5, 1e-4), X, Y)
+    post = orc.fit_gradient(X, Y, 5, 0.6, 1.5, 1e-4)
+    Xq = -2 + 4 * rng.random((7, 4))
+    ref = orc.posterior_cov(post, Xq)
+    cov = abo.posterior_grad_cov(gp, Xq)
+    assert cov.shape == (35, 35) and np.max(np.abs(cov - ref)) < 1e-9 * max(1.0, np.max(np.abs(ref)))
+    assert np.allclose(np.diag(cov), abo.posterior_grad_var(gp, Xq), rtol=0, atol=1e-11)
+    sgp = abo.update(abo.StandardGP(make_kernel(abo, 1, 0.6, 1.5), 1e-4), X, Y[:, 0])
+    spost = orc.fit_standard(X, Y[:, 0], 1, 0.6, 1.5, 1e-4)
+    assert np.max(np.abs(abo.posterior_cov(sgp, Xq) - orc.posterior_cov(spost, Xq))) < 1e-10
+
+
+# ---- GradientNormUCB and EnsembleAcquisition (gradNormUCB.jl:43-51, EnsembleAcq.jl:53-55) -----
+def test_grad_norm_ucb_and_ensemble(abo, orc):
+    rng = np.random.default_rng(9)
+    X = -2 + 4 * rng.random((30, 3)); Y = orc.rosenbrock_with_grad(X); Y = Y / np.std(Y[:, 0])
+    gp = abo.update(abo.GradientGP(make_kernel(abo, 3, 0.7, 1.2), 4, 1e-4), X, Y)
+    post = orc.fit_gradient(X, Y, 3, 0.7, 1.2, 1e-4)
+    Xq = -2 + 4 * rng.random((1500, 3))                      # spans two chunks of 1024 points
+    g = abo.GradientNormUCB(1.5)
+    val = g(gp, Xq)
+    ref = orc.grad_norm_ucb(post, Xq[:60], 1.5)
+    assert np.all(np.isfinite(val)) and close(val[:60], ref, np.max(np.abs(ref)), 1e-9)
+    ei = abo.ExpectedImprovement(0.01, float(Y[:, 0].min()))
+    ens = abo.EnsembleAcquisition([2.0, 6.0], [ei, g])          # test_acquisition.jl:223-253: weighted sum
+    assert np.allclose(ens.weights, [0.25, 0.75])
+    assert np.allclose(ens(gp, Xq[:100]), 0.25 * ei(gp, Xq[:100]) + 0.75 * val[:100], rtol=0, atol=1e-13)
+    s, ti, tv = ens.topk(gp, Xq[:200], 10)
+    assert list(ti) == list(orc.sortperm_rev(s, 10))
+    e2 = ens.update(Y, gp)
+    assert isinstance(e2.acquisitions[0], abo.ExpectedImprovement) and e2.acquisitions[0].best_y == float(Y[:, 0].min())
+    with pytest.raises(ValueError):
+        abo.EnsembleAcquisition([-1.0, 1.0], [ei, g])
+    dom = abo.ContinuousDomain([-2.0] * 3, [2.0] * 3)
+    x = abo.optimize_acquisition(ens, gp, dom, n_grid=500, n_local=2, rng=np.random.default_rng(0))
+    assert x.shape == (3,) and np.all(x >= dom.lower) and np.all(x <= dom.upper)
