@@ -16,7 +16,7 @@ from .acquisition import (AbstractAcquisition, EnsembleAcquisition, ExpectedImpr
                           ProbabilityImprovement, UpperConfidenceBound)
 from .domains import AbstractDomain, ContinuousDomain
 from .parallel import init_nccl_context, merge_topk, shard_range, sharded_topk, sync_posterior
-from .bayesian_opt import (BOStruct, latin_hypercube, lockstep_lbfgsb, optimize, optimize_acquisition, optimize_hyperparameters,
+from .bayesian_opt import (BOStruct, latin_hypercube, lengthscale_bounds, lockstep_lbfgsb, monte_carlo_fill_distance, optimize, optimize_acquisition, optimize_hyperparameters,
                            standardize_problem, stop_criteria, update_bo)
 
 

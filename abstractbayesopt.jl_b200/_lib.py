@@ -18,7 +18,7 @@ SYMBOLS = [
     "abo_version", "abo_last_error", "abo_ctx_create", "abo_ctx_destroy", "abo_ctx_device", "abo_ctx_stream",
     "abo_ctx_launch_count", "abo_ctx_profile", "abo_ctx_profile_read", "abo_debug_potf2_clocks", "abo_gp_create", "abo_gp_destroy", "abo_gp_set_params", "abo_gp_fit", "abo_gp_append",
     "abo_gp_clone", "abo_gp_n", "abo_gp_alpha", "abo_gp_factor", "abo_gp_posterior", "abo_gp_posterior_cov", "abo_acq_eval", "abo_acq_eval_dev", "abo_acq_eval_grad",
-    "abo_nlml_batch", "abo_potrf_dev", "abo_nccl_unique_id", "abo_ctx_init_rank", "abo_gp_sync",
+    "abo_nlml_batch", "abo_potrf_dev", "abo_fill_distance", "abo_nccl_unique_id", "abo_ctx_init_rank", "abo_gp_sync",
     "abo_topk_allgather",
 ]
 
@@ -80,6 +80,7 @@ def lib():
             "abo_acq_eval_grad": [vp, i32, vp, vp, i64, vp, vp, vp, vp],
             "abo_nlml_batch": [vp, vp, vp, i64, vp, i64, vp, vp, vp],
             "abo_potrf_dev": [vp, vp, i64, i64, C.POINTER(i64)],
+            "abo_fill_distance": [vp, vp, i64, i32, vp, i64, C.POINTER(C.c_double)],
             "abo_nccl_unique_id": [vp],
             "abo_ctx_init_rank": [vp, i32, i32, vp],
             "abo_gp_sync": [vp, i32],
@@ -144,6 +145,12 @@ class Context:
         ms = (C.c_double * 3)(); n = (C.c_int64 * 3)()
         check(lib().abo_ctx_profile_read(self._h, ms, n))
         return list(ms), list(n)
+
+    def fill_distance(self, X, S) -> float:
+        X = f64(X); S = f64(S)
+        out = C.c_double(0.0)
+        check(lib().abo_fill_distance(self._h, ptr(X), X.shape[0], X.shape[1], ptr(S), S.shape[0], C.byref(out)))
+        return out.value
 
     def potf2_clocks(self):
         out = (C.c_int64 * 16)()

@@ -26,6 +26,31 @@ def latin_hypercube(n, lower, upper, rng):
     return lower + (upper - lower) * u
 
 
+def monte_carlo_fill_distance(x_train, domain, n_samples=10_000, rng=None, ctx=None):
+    """monte_carlo_fill_distance (BO_utils.jl:140-159): the n_samples x n nearest-neighbour scan runs
+    on the device (abo_fill_distance); the uniform samples are drawn on the host."""
+    from ._lib import default_context
+    rng = np.random.default_rng() if rng is None else rng
+    X = np.asarray(x_train, dtype=np.float64).reshape(len(x_train), -1)
+    S = domain.lower + rng.random((n_samples, len(domain.lower))) * (domain.upper - domain.lower)
+    return (ctx or default_context()).fill_distance(X, S)
+
+
+def lengthscale_bounds(x_train, domain, min_frac=0.1, max_frac=1.0, n_samples=10_000, rng=None, ctx=None):
+    """lengthscale_bounds (BO_utils.jl:87-128): upper = max_frac * box side; lower = min_frac * fill
+    distance (Monte-Carlo for d > 1, exact largest gap incl. the domain edges for d = 1), floored at 1e-12."""
+    d = len(domain.lower)
+    X = np.asarray(x_train, dtype=np.float64).reshape(len(x_train), -1)
+    if X.shape[1] != d:
+        raise ValueError(f"All points in X_train must have dimension {d}")
+    upper = max_frac * (domain.upper - domain.lower)
+    if d > 1:
+        h = monte_carlo_fill_distance(X, domain, n_samples=n_samples, rng=rng, ctx=ctx)
+    else:
+        h = float(np.max(np.diff(np.concatenate([[domain.lower[0]], np.sort(X[:, 0]), [domain.upper[0]]]))))
+    return np.full(d, max(min_frac * h, 1e-12)), upper
+
+
 def optimize_acquisition(acqf, surrogate, domain, n_grid=10_000, n_local=100, rng=None, refine=True):
     """optimize_acquisition (acq_utils.jl:33-73): LHS grid → ONE batched, fused sweep that also
     returns the stable top-n_local (replaces acqf(...) + sortperm, :50-52) → box-constrained L-BFGS
@@ -146,9 +171,10 @@ def optimize_hyperparameters(model, x_train, y_train, old_params, scale_std=1.0,
     of one ForwardDiff evaluation per restart and step."""
     rng = np.random.default_rng() if rng is None else rng
     ls_lo, ls_hi = 1e-3, 1e3
-    if domain is not None:
-        side = float(np.max(domain.upper - domain.lower))
-        ls_lo, ls_hi = max(1e-6, 1e-3 * side), side
+    if domain is not None:                               # data-informed bounds (bayesian_opt.jl:216-228)
+        lL, lU = lengthscale_bounds(x_train, domain, rng=rng, ctx=model.ctx)
+        ls_lo, ls_hi = max(float(np.min(lL)), 1e-6), float(np.max(lU))
+        assert ls_lo < ls_hi
     sc_lo, sc_hi = 1e-3 / scale_std ** 2, 1e6 / scale_std ** 2
     lo = np.log([ls_lo, sc_lo]); hi = np.log([ls_hi, sc_hi])
     eps2 = 2 * np.finfo(float).eps

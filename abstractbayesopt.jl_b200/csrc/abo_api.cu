@@ -51,6 +51,7 @@ static int configure_kernels() {
     CU(cudaFuncSetAttribute(gemm_small_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<32, 4>::SMEM_BYTES));
     CU(cudaFuncSetAttribute(gemm_small_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<32, 8>::SMEM_BYTES));
     CU(cudaFuncSetAttribute(gemm_small_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<64, 8>::SMEM_BYTES));
+    CU(cudaFuncSetAttribute(fill_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 96 * 8));
     CU(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM_BYTES));
     CU(cudaFuncSetAttribute(potf2_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_BYTES));
     CU(cudaFuncSetAttribute(sweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
@@ -1050,6 +1051,31 @@ extern "C" int32_t abo_acq_eval_dev(abo_gp* g, int32_t acq_id, const double* par
     if (m == 0) return ABO_OK;
     CU(cudaSetDevice(g->ctx->device));
     return acq_eval_common(g, acq_id, params, d_Xc, m, d_scores, nullptr, k, top_idx, top_val);
+}
+
+extern "C" int32_t abo_fill_distance(abo_ctx* c, const double* X, int64_t n, int32_t d, const double* S, int64_t m,
+                                     double* h_fill) {
+    if (!c || !X || !S || !h_fill) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (n < 1 || m < 1 || d < 1 || d > 96) return abo_fail(ABO_ERR_INVALID, "bad sizes (d <= 96)");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int nblk = (int)((m + 255) / 256);
+    double *dX, *dS, *dB;
+    int rc;
+    if ((rc = ws_get(c, WS_STAGE_X, sizeof(double) * (size_t)n * d, (void**)&dX))) return rc;
+    if ((rc = ws_get(c, WS_CAND, sizeof(double) * (size_t)m * d, (void**)&dS))) return rc;
+    if ((rc = ws_get(c, WS_OUT_A, sizeof(double) * (size_t)nblk, (void**)&dB))) return rc;
+    CU(cudaMemcpyAsync(dX, X, sizeof(double) * n * d, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dS, S, sizeof(double) * m * d, cudaMemcpyHostToDevice, st));
+    fill_distance_kernel<<<nblk, 256, sizeof(double) * 256 * d, st>>>(dX, n, d, dS, m, dB);
+    KL(c);
+    std::vector<double> hb(nblk);
+    CU(cudaMemcpyAsync(hb.data(), dB, sizeof(double) * nblk, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    double r = 0.0;
+    for (double v : hb) r = std::max(r, v);
+    *h_fill = r;
+    return ABO_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1233,3 +1233,40 @@ __global__ void cov_finish_kernel(KSpec spec, const double* __restrict__ Xc, int
     cov[t] = (prior - G[((int64_t)b * mp + c) * ldg + (int64_t)b2 * mp + c2]) + (r == q ? JITTER : 0.0);
 }
 }  // namespace abo
+
+// fill distance  max_s min_j || x_s - X_j ||  (monte_carlo_fill_distance, src/BO_utils.jl:140-159):
+// one thread per sample, training points streamed through shared memory; block maxima out.
+namespace abo {
+__global__ void __launch_bounds__(256) fill_distance_kernel(const double* __restrict__ X, int64_t n, int d,
+                                                            const double* __restrict__ S, int64_t m,
+                                                            double* __restrict__ blockmax) {
+    extern __shared__ double sx[];                      // [tile][d]
+    __shared__ double red[8];
+    const int tile = 256;
+    const int64_t sidx = blockIdx.x * 256LL + threadIdx.x;
+    double best = CUDART_INF;
+    for (int64_t j0 = 0; j0 < n; j0 += tile) {
+        const int cnt = (int)((n - j0 < tile) ? (n - j0) : tile);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt * d; e += 256) sx[e] = X[j0 * d + e];
+        __syncthreads();
+        if (sidx < m) {
+            for (int j = 0; j < cnt; ++j) {
+                double u = 0.0;
+                for (int k = 0; k < d; ++k) { const double df = sx[j * d + k] - S[sidx * d + k]; u = fma(df, df, u); }
+                best = fmin(best, u);
+            }
+        }
+    }
+    double v = (sidx < m) ? sqrt(best) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = red[0];
+        for (int w = 1; w < 8; ++w) r = fmax(r, red[w]);
+        blockmax[blockIdx.x] = r;
+    }
+}
+}  // namespace abo

@@ -139,6 +139,11 @@ int32_t abo_acq_eval_grad(abo_gp* gp, int32_t acq_id, const double* params, cons
 int32_t abo_nlml_batch(abo_gp* gp, const double* X, const double* y, int64_t n,
                        const double* logparams, int64_t R, double* nlml, double* grad, int32_t* info);
 
+/* monte_carlo_fill_distance (src/BO_utils.jl:140-159): max over the m sample points S (m x d) of the
+ * distance to the nearest of the n training points X (n x d); the caller draws the samples. */
+int32_t abo_fill_distance(abo_ctx* ctx, const double* X, int64_t n, int32_t d, const double* S, int64_t m,
+                          double* h_fill);
+
 /* ---- standalone factorisation entry (Cholesky TFLOP/s metric; A is n x n row-major, lower
  *      triangle referenced, overwritten by L on device; d_A device pointer, ld >= n) ---------- */
 int32_t abo_potrf_dev(abo_ctx* ctx, double* d_A, int64_t n, int64_t ld, int64_t* info);

@@ -498,3 +498,24 @@ def test_grad_norm_ucb_and_ensemble(abo, orc):
     dom = abo.ContinuousDomain([-2.0] * 3, [2.0] * 3)
     x = abo.optimize_acquisition(ens, gp, dom, n_grid=500, n_local=2, rng=np.random.default_rng(0))
     assert x.shape == (3,) and np.all(x >= dom.lower) and np.all(x <= dom.upper)
+
+
+# ---- lengthscale_bounds / monte_carlo_fill_distance (BO_utils.jl:87-159; test_bayesian_opt.jl:419-456)
+def test_fill_distance_and_lengthscale_bounds(abo):
+    rng = np.random.default_rng(0)
+    dom = abo.ContinuousDomain([0.0, -1.0, 2.0], [1.0, 1.0, 5.0])
+    X = dom.lower + rng.random((700, 3)) * (dom.upper - dom.lower)
+    S = dom.lower + rng.random((5000, 3)) * (dom.upper - dom.lower)
+    ref = max(np.sqrt(np.min(np.sum((X - s) ** 2, axis=1))) for s in S)
+    assert abs(abo.default_context().fill_distance(X, S) - ref) <= 1e-15 * ref * 4
+    lo, up = abo.lengthscale_bounds(X, dom, rng=np.random.default_rng(1))
+    assert np.array_equal(up, dom.upper - dom.lower) and np.all(lo == lo[0]) and 0 < lo[0] < 0.1 * np.max(up)
+    # 1-D: exact largest gap including the domain edges (test_bayesian_opt.jl:419-440)
+    d1 = abo.ContinuousDomain([0.0], [1.0])
+    lo1, up1 = abo.lengthscale_bounds([0.1, 0.5, 0.6], d1)
+    assert abs(lo1[0] - 0.1 * 0.4) < 1e-15 and up1[0] == 1.0
+    # 2-D Monte-Carlo estimate close to the analytic fill distance of a regular grid (atol 1e-2)
+    g = np.array([[i, j] for i in (0.25, 0.75) for j in (0.25, 0.75)])
+    d2 = abo.ContinuousDomain([0.0, 0.0], [1.0, 1.0])
+    h = abo.monte_carlo_fill_distance(g, d2, n_samples=20000, rng=np.random.default_rng(2))
+    assert abs(h - math.sqrt(2) * 0.25) < 1e-2
