@@ -107,11 +107,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def cpu_restatement_throughput(sample_m, seed=42):
     """Oracle (CPU restatement of the reference path) on a bounded sample of the C4 workload:
     conditioning is untimed set-up, the timed part is posterior mean + variance + EI over
     `sample_m` candidates (best of 2 after one warm-up), all host cores."""
     from oracle import abo_oracle as orc
+    use_all_host_cores()
     c = orc.make_config("C4", seed=seed, n=N_OBS, m=sample_m, d=DIM)
     t0 = time.perf_counter()
     post = orc.fit_standard(c["X"], c["y"], c["kind"], c["inv_ls"], c["scale"], c["noise"])
@@ -136,8 +146,8 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     sample = args.cpu_sample
-    vals, tms = [], []
     from oracle import abo_oracle as orc
+    use_all_host_cores()
     c = orc.make_config("C4", n=N_OBS, m=sample, d=DIM)
     post = orc.fit_standard(c["X"], c["y"], c["kind"], c["inv_ls"], c["scale"], c["noise"])
     best = float(c["y"].min())
@@ -206,7 +216,21 @@ def main():
     model = abo.StandardGP(c["scale"] * abo.with_lengthscale(abo.SqExponentialKernel(), 1.0 / c["inv_ls"]), c["noise"],
                            ctx=ctx)
     t0 = time.perf_counter()
-    model = abo.update(model, c["X"], c["y"])
+    t_sync = None
+    if world == 1:
+        model = abo.update(model, c["X"], c["y"])
+    else:
+        # rank 0 conditions the surrogate; L, L^-1, X, alpha and the hyper-parameters reach the other
+        # ranks with one NCCL broadcast over NVLink (abo_gp_sync) — set-up, outside the timed region
+        abo.init_nccl_context(ctx)
+        model = abo.update(model, c["X"], c["y"]) if rank == 0 else abo.empty_posterior_like(model, d)
+        torch.cuda.synchronize(); dist.barrier()
+        abo.sync_posterior(model, 0)                 # first call also sets the NCCL channels up
+        torch.cuda.synchronize(); dist.barrier()
+        ts = time.perf_counter()
+        abo.sync_posterior(model, 0)
+        torch.cuda.synchronize(); dist.barrier()
+        t_sync = time.perf_counter() - ts
     t_fit = time.perf_counter() - t0
     acq = abo.ExpectedImprovement(0.01, float(c["y"].min()))
     params = acq.params()
@@ -356,6 +380,9 @@ def main():
                     "topk_matches_device_run": same_top},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "posterior_broadcast": None if t_sync is None else {
+                "bytes": 2 * Npad * Npad * 8, "ms": 1e3 * t_sync, "gb_per_s": 2 * Npad * Npad * 8 / t_sync / 1e9,
+                "how": "abo_gp_sync: NCCL broadcast of L and L^-1 (+ X, alpha) from rank 0, second call"},
             "cholesky": chol,
             "cpu_baseline": cpu,
         }
