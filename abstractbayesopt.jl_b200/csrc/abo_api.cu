@@ -47,16 +47,12 @@ static int configure_kernels() {
     CU(configure_gemm<KC, KC, EPI_STORE>());
     CU(configure_gemm<KC, MC, EPI_STORE>());
     CU(configure_gemm<MC, MC, EPI_STORE>());
-    CU(configure_gemm<KC, KC, EPI_SUMSQ>());
-    CU(cudaFuncSetAttribute(gemm_small_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<32, 4>::SMEM_BYTES));
     CU(cudaFuncSetAttribute(gemm_small_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<32, 8>::SMEM_BYTES));
     CU(cudaFuncSetAttribute(gemm_small_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<64, 8>::SMEM_BYTES));
     CU(cudaFuncSetAttribute(fill_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 96 * 8));
-    CU(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM_BYTES));
     CU(cudaFuncSetAttribute(potf2_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_BYTES));
     CU(cudaFuncSetAttribute(sweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
     CU(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
-    CU(cudaFuncSetAttribute(syrk_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
     return ABO_OK;
 }
 
@@ -301,10 +297,8 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
     const int T = (int)(Npad / NB);
     static const int OB_env = getenv("ABO_POTRF_OB") ? atoi(getenv("ABO_POTRF_OB")) : 3;
     static const bool one_stream = getenv("ABO_POTRF_1STREAM") != nullptr;
-    static const bool use_ws = getenv("ABO_POTF2_V6") == nullptr;
     static const bool pdl_on = getenv("ABO_NO_PDL") == nullptr;
     static const bool ramp = getenv("ABO_POTRF_NORAMP") == nullptr;
-    static const int reserve = getenv("ABO_POTRF_RESERVE") ? atoi(getenv("ABO_POTRF_RESERVE")) : -1;
     // panel GEMMs: 64-row tiles while the panel is tall (throughput), 32-row tiles once it is short (latency)
     static const int big_rem = getenv("ABO_POTRF_BIGREM") ? atoi(getenv("ABO_POTRF_BIGREM")) : 4096;
     const int OB = std::max(1, OB_env);
@@ -333,8 +327,7 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
         for (int jp = Jb; jp < je; ++jp) {
             double* Ajj = A + (int64_t)jp * NB * (ld + 1);
             double* Dj = Dinv + (int64_t)jp * NB * NB;
-            if (use_ws) CU(launch_pdl(potf2_ws_kernel, dim3(1), dim3(512), PW_SMEM_BYTES, sp, pdl, Ajj, ld, (int64_t)0, Dj, (int64_t)0, info, jp * NB));
-            else potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM_BYTES, sp>>>(Ajj, ld, 0, Dj, 0, info, jp * NB);
+            CU(launch_pdl(potf2_ws_kernel, dim3(1), dim3(512), PW_SMEM_BYTES, sp, pdl, Ajj, ld, (int64_t)0, Dj, (int64_t)0, info, jp * NB));
             KL(c);
             const int rem = (T - jp - 1) * NB;
             if (rem <= 0) break;
@@ -367,15 +360,7 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
             CU(cudaStreamWaitEvent(su, c->ev_a, 0));
             u.row_t0 = jn; u.col_t0 = jn;
             mark(su);
-            if (reserve >= 0) {      // persistent U_rest on (SMs - reserve) CTAs; the panel stream keeps the rest
-                SyrkPersistParams up;
-                up.C = A; up.ld = ld; up.t0 = jn; up.T = T; up.kcol0 = u.kcol0; up.nk = u.nk;
-                const int ntl = (T - jn) * (T - jn + 1) / 2;
-                const int grid = std::max(1, std::min(ntl, c->sms - reserve));
-                syrk_persist_kernel<<<grid, SW_THREADS, SW_SMEM_BYTES, su>>>(tmL, up);
-            } else {
-                syrk_tma_kernel<<<dim3(T - jn, T - jn), SW_THREADS, SY_SMEM_BYTES, su>>>(tmL, u);
-            }
+            syrk_tma_kernel<<<dim3(T - jn, T - jn), SW_THREADS, SY_SMEM_BYTES, su>>>(tmL, u);
             KL(c);
             mark(su);
         }
@@ -695,15 +680,9 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
     const int64_t Npad = g->Npad;
     const int T = (int)(Npad / NB);
     // chunk: enough tiles per launch (>= ~2048) that the persistent kernel's tail is small, K* buffer
-    // bounded by 512 MB.  (v1 kernel, ABO_SWEEP_V1=1: L2-resident 64 MB chunks.)
-    static const bool use_v1 = getenv("ABO_SWEEP_V1") != nullptr;
-    int64_t mc;
-    if (use_v1) {
-        mc = ((int64_t)(64ll << 20) / (Npad * 8)) / NB * NB;
-    } else {
-        mc = (int64_t)NB * ((2048 + T - 1) / T);
-        mc = std::min<int64_t>(mc, ((int64_t)(512ll << 20) / (Npad * 8)) / NB * NB);
-    }
+    // bounded by 512 MB
+    int64_t mc = (int64_t)NB * ((2048 + T - 1) / T);
+    mc = std::min<int64_t>(mc, ((int64_t)(512ll << 20) / (Npad * 8)) / NB * NB);
     mc = std::max<int64_t>(NB, std::min<int64_t>(mc, 65536));
     mc = std::min<int64_t>(mc, (m + NB - 1) / NB * NB);
     const int64_t vpts = (Npad + g->p - 1) / g->p;                 // virtual points incl. padding columns
@@ -714,7 +693,7 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
     // default (it doubles the K* workspace).
     const int64_t nchunks = (m + mc - 1) / mc;
     static const bool want_overlap = getenv("ABO_SWEEP_OVERLAP") != nullptr;
-    const bool overlap = !use_v1 && !c->profile && nchunks > 1 && want_overlap;
+    const bool overlap = !c->profile && nchunks > 1 && want_overlap;
     const int nbuf = overlap ? 2 : 1;
     double *KsAll, *pmeanAll, *sumsq;
     int rc;
@@ -724,11 +703,9 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
     double* KsB[2] = {KsAll, KsAll + (size_t)mc * Npad * (nbuf - 1)};
     double* pmB[2] = {pmeanAll, pmeanAll + (size_t)npb * mc * (nbuf - 1)};
     CUtensorMap tmA, tmB[2];
-    if (!use_v1) {
-        if ((rc = make_tmap_k4(&tmA, g->dLinv, Npad, Npad, g->ld))) return rc;
-        for (int q = 0; q < nbuf; ++q)
-            if ((rc = make_tmap_k4(&tmB[q], KsB[q], Npad, mc, Npad))) return rc;
-    }
+    if ((rc = make_tmap_k4(&tmA, g->dLinv, Npad, Npad, g->ld))) return rc;
+    for (int q = 0; q < nbuf; ++q)
+        if ((rc = make_tmap_k4(&tmB[q], KsB[q], Npad, mc, Npad))) return rc;
     AcqSpec a;
     a.acq = acq;
     a.p0 = params ? params[0] : 0.0;
@@ -779,20 +756,9 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
             if ((rc = prof_mark(c))) return rc;
         }
         if ((rc = prof_mark(c))) return rc;
-        if (use_v1) {
-            GemmParams p{};
-            p.A = g->dLinv; p.lda = g->ld;
-            p.B = KsB[buf]; p.ldb = Npad;
-            p.M = (int)Npad; p.N = (int)mc_eff; p.K = (int)Npad;
-            p.flags = KHI_M | REV_M;
-            p.sumsq = sumsq; p.sumsq_ld = mc;
-            CU((launch_gemm<KC, KC, EPI_SUMSQ>(p, 1, st)));
-        } else {
-            SweepParams sp;
-            sp.T = T; sp.ncb = (int)(mc_eff / NB); sp.sumsq = sumsq; sp.sumsq_ld = mc;
-            const int grid = std::min(c->sms, sp.T * sp.ncb);
-            sweep_tma_kernel<<<grid, SW_THREADS, SW_SMEM_BYTES, st>>>(tmA, tmB[buf], sp);
-        }
+        SweepParams sp;
+        sp.T = T; sp.ncb = (int)(mc_eff / NB); sp.sumsq = sumsq; sp.sumsq_ld = mc;
+        sweep_tma_kernel<<<std::min(c->sms, sp.T * sp.ncb), SW_THREADS, SW_SMEM_BYTES, st>>>(tmA, tmB[buf], sp);
         KL(c);
         if ((rc = prof_mark(c))) return rc;
         if ((rc = prof_mark(c))) return rc;

@@ -1,7 +1,8 @@
 // gemm_dmma.cuh — FP64 tensor-core (DMMA.8x8x4) tile engine shared by every O(n^3) step of the
 // path: SYRK trailing update and panel TRSM of the blocked Cholesky, the triangular inverse,
-// K^-1 = L^-T L^-1 for the NLML gradient, and the candidate sweep  W = L^-1 K*  with a fused
-// column sum-of-squares epilogue (posterior variance).
+// K^-1 = L^-T L^-1 for the NLML gradient and the W = L^-1 K*, Z = L^-T W products of the
+// acquisition-gradient path.  (The candidate sweep itself runs on the TMA/mbarrier kernel of
+// sweep_tma.cuh, which shares the shared-memory tile layout and the DMMA inner loop.)
 //
 // tcgen05 has no f64 kind, so on sm_100a FP64 tensor work is the warp-level
 // mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; the m16n8k{4,8,16} PTX shapes lower to the same SASS
@@ -25,13 +26,12 @@ constexpr int TILE_DOUBLES = 16 * 132;   // per operand per stage (covers both l
 constexpr int GEMM_SMEM_BYTES = STAGES * 2 * TILE_DOUBLES * (int)sizeof(double);
 
 enum Layout { KC = 0, MC = 1 };
-enum Epilogue { EPI_STORE = 0, EPI_SUMSQ = 1 };
+enum Epilogue { EPI_STORE = 0 };
 enum GemmFlags {
     KLO_M = 1,        // k starts at the tile's first row      (A^T-type lower operands)
     KLO_N = 2,        // k starts at the tile's first column   (B lower triangular, k >= n)
     KHI_M = 4,        // k stops after the tile's last row     (A lower triangular, k <= m)
-    LOWER_ONLY = 8,   // skip tiles strictly above the diagonal
-    REV_M = 16        // launch the heaviest (largest m) tiles first
+    LOWER_ONLY = 8    // skip tiles strictly above the diagonal
 };
 
 struct GemmParams {
@@ -41,8 +41,6 @@ struct GemmParams {
     int M, N, K;                         // multiples of 128 / 128 / 16
     double alpha, beta;
     int flags;
-    double* sumsq;                       // EPI_SUMSQ: [M/128][sumsq_ld] partial column sums of squares
-    int64_t sumsq_ld, strideS;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -98,8 +96,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmParams p
     double* sB = smem + STAGES * TILE_DOUBLES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
-    const int mt_idx = (p.flags & REV_M) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
-    const int m0 = mt_idx * BM, n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     if ((p.flags & LOWER_ONLY) && n0 > m0) return;
 
     const double* A = p.A + (int64_t)blockIdx.z * p.strideA;
@@ -174,29 +171,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmParams p
                 }
                 *dst = v;
             }
-        }
-    } else {
-        // column sums of squares of this 128 x 128 tile -> sumsq[m-tile][n0 + col]
-        __syncthreads();                      // everyone is done with the pipeline buffers
-        double* red = smem;                   // [4][128]
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                double s = 0.0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) s = fma(acc[i][j][e], acc[i][j][e], s);
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                s += __shfl_xor_sync(0xffffffffu, s, 8);
-                s += __shfl_xor_sync(0xffffffffu, s, 16);
-                if ((lane >> 2) == 0) red[(warp & 3) * 128 + wn + j * 8 + 2 * (lane & 3) + e] = s;
-            }
-        }
-        __syncthreads();
-        if (tid < 128) {
-            double s = ((red[tid] + red[128 + tid]) + red[256 + tid]) + red[384 + tid];
-            double* out = p.sumsq + (int64_t)blockIdx.z * p.strideS;
-            out[(int64_t)mt_idx * p.sumsq_ld + n0 + tid] = s;
         }
     }
 }

@@ -128,265 +128,18 @@ __global__ void __launch_bounds__(256) kmat_kernel(KSpec spec, const double* __r
 }
 
 // ------------------------------------------------------------------------------------------
-// 128 x 128 diagonal block:  A = L L^T in shared memory (right-looking), then L^-1 by
-// recursive doubling (8 -> 16 -> ... -> 128).  Writes L (upper part zeroed) back in place and
-// L^-1 to Dinv.  A non-positive pivot sets *info (1-based global pivot, first failure wins).
-// One CTA of POTF2_THREADS threads per matrix (blockIdx.x = batch).
+// 128 x 128 diagonal block of the blocked Cholesky:  A = L L^T in shared memory and L^-1 of the
+// block.  Writes L (upper part zeroed) back in place and L^-1 to Dinv.  A non-positive pivot
+// sets *info (1-based global pivot, first failure wins).  One CTA of 512 threads per matrix
+// (blockIdx.x = batch).
 // ------------------------------------------------------------------------------------------
-__device__ long long g_potf2_clk[16];     // phase timestamps of the last potf2_inv CTA 0 (inspection)
-constexpr int POTF2_THREADS = 512;
-constexpr int POTF2_WARPS = POTF2_THREADS / 32;
-constexpr int POTF2_LD = 129;
+__device__ long long g_potf2_clk[16];     // phase timestamps of CTA 0 of the last launch (inspection)
+constexpr int POTF2_LD = 129;                                    // block [128][129]
 constexpr int POTF2_PLD = 132;                                   // sub-panel buffer [32][132]
-constexpr int POTF2_SCRATCH = 64 * 68;                           // >= 32*132 + 96 and >= 64*(b+4) for b <= 64
-constexpr int POTF2_SMEM_BYTES = (128 * POTF2_LD + POTF2_SCRATCH + 32 * 32 + 16) * (int)sizeof(double);
-
-__global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __restrict__ Ablk, int64_t ld, int64_t strideA,
-                                                                  double* __restrict__ Dinv, int64_t strideD,
-                                                                  int* __restrict__ info, int pivot_base) {
-    extern __shared__ __align__(16) double sm[];
-    double* sL = sm;                       // [128][129]
-    double* sT = sm + 128 * POTF2_LD;      // scratch: sub-panel columns, then T of the inverse levels
-    __shared__ int s_fail;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
-    double* A = Ablk + (int64_t)blockIdx.x * strideA;
-    double* Di = Dinv + (int64_t)blockIdx.x * strideD;
-    if (tid == 0) s_fail = 0;
-    const bool stamp = (tid == 0 && blockIdx.x == 0);
-    if (stamp) g_potf2_clk[0] = clock64();
-    for (int e = tid; e < 128 * 128; e += POTF2_THREADS) {
-        int r = e >> 7, c = e & 127;
-        sL[r * POTF2_LD + c] = A[(int64_t)r * ld + c];
-    }
-    __syncthreads();
-    if (stamp) g_potf2_clk[1] = clock64();
-
-    // ---- Cholesky: four 32-column sub-panels, no block barrier inside the column loop.
-    //  (1) warp 0 factors the 32x32 diagonal block in REGISTERS (lane = row).  Column j of L is
-    //      broadcast through shared memory; the NEXT pivot only needs the lane's own entry
-    //      (a_{j+1,j+1} - l_{j+1,j}^2), so it is formed and shuffled out before the rest of the
-    //      column update: the rsqrt/shuffle latency chain overlaps the update's issue slots.
-    //  (2) warps 1.. solve the rows below against it (lane = row, right-looking substitution,
-    //      L entries broadcast from shared memory) and stage the panel in a conflict-free buffer;
-    //  (3) all warps apply the rank-32 update to the rest of the block with DMMA tiles.
-    double* sRinv = sT + POTF2_SCRATCH - 32;                   // reciprocals of the block's diagonal
-    double* sCol = sT + POTF2_SCRATCH - 96;                    // two 32-entry column buffers (ping-pong)
-    double* sDT = sT + POTF2_SCRATCH;                          // transposed diagonal block [32][32]
-    for (int sp = 0; sp < 4; ++sp) {
-        const int c0 = sp * 32, c1 = c0 + 32;
-        if (warp == 0) {
-            double a[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) a[c] = sL[(c0 + lane) * POTF2_LD + c0 + c];
-            int failcol = -1;
-            double d = __shfl_sync(0xffffffffu, a[0], 0);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (failcol < 0 && !(d > 0.0)) failcol = j;      // uniform across the warp; keep going
-                const double rinv = rsqrt(d);                    // (garbage after a failure is discarded)
-                const double lj = (lane == j) ? d * rinv : a[j] * rinv;
-                a[j] = lj;
-                if (j < 31) {                                    // next pivot, ahead of the column update
-                    const double own = fma(-lj, lj, a[(j + 1) & 31]);
-                    d = __shfl_sync(0xffffffffu, own, (j + 1) & 31);
-                }
-                if (lane == j) sRinv[j] = rinv;
-                double* col = sCol + (j & 1) * 32;               // column j of L, broadcast through smem
-                col[lane] = lj;
-                __syncwarp();
-                // rows above the diagonal carry garbage that is never consumed: no predicate needed.
-                // Column entries are fetched two at a time (LDS.128).
-#pragma unroll
-                for (int c2 = 0; c2 < 16; ++c2) {
-                    if (2 * c2 + 1 > j) {
-                        const double2 lc = *reinterpret_cast<const double2*>(col + 2 * c2);
-                        if (2 * c2 > j) a[2 * c2] = fma(-lj, lc.x, a[2 * c2]);
-                        a[2 * c2 + 1] = fma(-lj, lc.y, a[2 * c2 + 1]);
-                    }
-                }
-            }
-            if (failcol >= 0) {
-                if (lane == 0) { s_fail = 1; atomicCAS(info + blockIdx.x, 0, pivot_base + c0 + failcol + 1); }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    if (c <= lane) sL[(c0 + lane) * POTF2_LD + c0 + c] = a[c];
-                    sDT[c * 32 + lane] = (c <= lane) ? a[c] : 0.0;      // transposed copy: [column j][row c]
-                }
-            }
-        }
-        __syncthreads();
-        if (stamp && sp == 0) g_potf2_clk[8] = clock64();
-        if (s_fail) break;
-        if (c1 >= 128) break;
-        {   // (2) rows below: x = a * inv(D)^T by substitution
-            const int r = c1 + (warp - 1) * 32 + lane;
-            if (warp >= 1 && r < 128) {
-                double x[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) x[c] = sL[r * POTF2_LD + c0 + c];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    x[j] *= sRinv[j];
-#pragma unroll
-                    for (int c2 = 0; c2 < 16; ++c2) {
-                        if (2 * c2 + 1 > j) {
-                            const double2 lc = *reinterpret_cast<const double2*>(sDT + j * 32 + 2 * c2);
-                            if (2 * c2 > j) x[2 * c2] = fma(-x[j], lc.x, x[2 * c2]);
-                            x[2 * c2 + 1] = fma(-x[j], lc.y, x[2 * c2 + 1]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < 32; ++c) { sL[r * POTF2_LD + c0 + c] = x[c]; sT[c * POTF2_PLD + r] = x[c]; }
-            }
-        }
-        __syncthreads();
-        if (stamp && sp == 0) g_potf2_clk[9] = clock64();
-        // (3) trailing update of rows/cols >= c1 with the panel columns [c0, c1): lower 16x16 tiles
-        const int nt = (128 - c1) / 16;
-        const int ntile = nt * (nt + 1) / 2;
-        for (int t = warp; t < ntile; t += POTF2_WARPS) {
-            int ti = 0, acc_t = t;
-            while (acc_t > ti) { acc_t -= ti + 1; ++ti; }
-            const int tj = acc_t;
-            const int r0 = c1 + 16 * ti, q0 = c1 + 16 * tj;
-            double cacc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-                double a[2], b[2];
-#pragma unroll
-                for (int mi = 0; mi < 2; ++mi) a[mi] = sT[(4 * kk + fk) * POTF2_PLD + r0 + 8 * mi + fr];
-#pragma unroll
-                for (int ni = 0; ni < 2; ++ni) b[ni] = sT[(4 * kk + fk) * POTF2_PLD + q0 + 8 * ni + fr];
-#pragma unroll
-                for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < 2; ++ni) dmma8x8x4(cacc[mi][ni][0], cacc[mi][ni][1], a[mi], b[ni]);
-            }
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 2; ++ni) {
-                    double* dst = sL + (r0 + 8 * mi + fr) * POTF2_LD + q0 + 8 * ni + 2 * fk;
-                    dst[0] -= cacc[mi][ni][0];
-                    dst[1] -= cacc[mi][ni][1];
-                }
-        }
-        __syncthreads();
-        if (stamp && sp == 0) g_potf2_clk[10] = clock64();
-    }
-    __syncthreads();
-    if (stamp) g_potf2_clk[2] = clock64();
-    const bool failed = s_fail != 0;
-    // write L back (zero strictly-upper part so that later k-ranges may overrun the diagonal tile)
-    for (int e = tid; e < 128 * 128; e += POTF2_THREADS) {
-        int r = e >> 7, c = e & 127;
-        A[(int64_t)r * ld + c] = (c <= r) ? sL[r * POTF2_LD + c] : 0.0;
-    }
-    if (failed) {                           // leave a harmless identity as the inverse
-        for (int e = tid; e < 128 * 128; e += POTF2_THREADS) Di[e] = ((e >> 7) == (e & 127)) ? 1.0 : 0.0;
-        return;
-    }
-    __syncthreads();
-    if (stamp) g_potf2_clk[3] = clock64();
-
-    // ---- inverse, level 0: sixteen 8x8 diagonal blocks, one thread per column
-    double x[8];
-    if (tid < 128) {
-        const int o = (tid >> 3) * 8, c = tid & 7;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            double sacc = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (k < i && k >= c) sacc = fma(-sL[(o + i) * POTF2_LD + o + k], x[k], sacc);
-            x[i] = (i >= c) ? sacc / sL[(o + i) * POTF2_LD + o + i] : 0.0;
-        }
-    }
-    __syncthreads();
-    if (tid < 128) {
-        const int o = (tid >> 3) * 8, c = tid & 7;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sL[(o + i) * POTF2_LD + o + c] = x[i];
-    }
-    __syncthreads();
-    if (stamp) g_potf2_clk[4] = clock64();
-    // ---- levels b = 8 .. 64:  X21 = -X22 * (L21 * X11), both products as DMMA 8x8 tiles that
-    //      skip the structurally zero k-ranges; T is staged in scratch with row stride b + 4.
-    for (int b = 8; b < 128; b <<= 1) {
-        const int tb = b >> 3;                           // 8x8 tiles per block side
-        const int tpp = tb * tb;                         // tiles per pair
-        const int ntl = (64 / b) * tpp;                  // tiles over all pairs
-        const int ST = b + 4;
-        // a warp owns a strip of up to four 8x8 tiles in one tile row (shared A fragment, four
-        // independent DMMA chains: the ~100-cycle DMMA latency is hidden by ILP, not by warps)
-        const int tjg_n = (tb + 3) >> 2;                 // strips per tile row
-        const int nstrip = (64 / b) * tb * tjg_n;
-        for (int g = warp; g < nstrip; g += POTF2_WARPS) {
-            const int pair = g / (tb * tjg_n), rem = g - pair * (tb * tjg_n), ti = rem / tjg_n, tj0 = (rem - ti * tjg_n) * 4;
-            const int o = pair * 2 * b;
-            double cc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-            const double* arow = sL + (o + b + ti * 8 + fr) * POTF2_LD + o + fk;
-            for (int k = tj0 * 8; k < b; k += 4) {       // X11[k][n] = 0 for k < n
-                const double a = arow[k];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (tj0 + q < tb && k >= (tj0 + q) * 8) {
-                        const double bv = sL[(o + k + fk) * POTF2_LD + o + (tj0 + q) * 8 + fr];
-                        dmma8x8x4(cc[q][0], cc[q][1], a, bv);
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (tj0 + q < tb) {
-                    double* dst = sT + pair * b * ST + (ti * 8 + fr) * ST + (tj0 + q) * 8 + 2 * fk;
-                    dst[0] = cc[q][0];
-                    dst[1] = cc[q][1];
-                }
-            }
-        }
-        __syncthreads();
-        for (int g = warp; g < nstrip; g += POTF2_WARPS) {
-            const int pair = g / (tb * tjg_n), rem = g - pair * (tb * tjg_n), ti = rem / tjg_n, tj0 = (rem - ti * tjg_n) * 4;
-            const int o = pair * 2 * b;
-            double cc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-            const double* arow = sL + (o + b + ti * 8 + fr) * POTF2_LD + o + b + fk;
-            const double* tcol = sT + pair * b * ST + fk * ST + fr;
-            for (int k = 0; k < (ti + 1) * 8; k += 4) {  // X22[m][k] = 0 for k > m
-                const double a = arow[k];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (tj0 + q < tb) {
-                        const double bv = tcol[k * ST + (tj0 + q) * 8];
-                        dmma8x8x4(cc[q][0], cc[q][1], a, bv);
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (tj0 + q < tb) {
-                    double* dst = sL + (o + b + ti * 8 + fr) * POTF2_LD + o + (tj0 + q) * 8 + 2 * fk;
-                    dst[0] = -cc[q][0];
-                    dst[1] = -cc[q][1];
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (stamp) g_potf2_clk[5] = clock64();
-    for (int e = tid; e < 128 * 128; e += POTF2_THREADS) {
-        int r = e >> 7, c = e & 127;
-        Di[e] = (c <= r) ? sL[r * POTF2_LD + c] : 0.0;
-    }
-    if (stamp) g_potf2_clk[6] = clock64();
-}
 
 // ------------------------------------------------------------------------------------------
-// potf2_ws_kernel — warp-specialised version of the diagonal-block kernel: the FACTOR group
-// (warps 0-7) runs the Cholesky of the 128 x 128 block exactly as potf2_inv_kernel does, while
+// potf2_ws_kernel — warp-specialised diagonal-block kernel: the FACTOR group (warps 0-7) runs the
+// Cholesky of the 128 x 128 block (four 32-column sub-panels, see the comments inside), while
 // the INVERSE group (warps 8-15) builds L^-1 one 32-row block behind it:
 //     round s (after the diagonal block D_s is final):
 //        X_ss = inv(D_s)                              (8x8 scalar level + two DMMA levels)

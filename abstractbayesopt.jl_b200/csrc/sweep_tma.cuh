@@ -297,122 +297,4 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmL, SyrkParams p) {
 }
 
 
-// ------------------------------------------------------------------------------------------
-// Persistent variant for the big U_rest update of the look-ahead Cholesky: all lower tiles of
-// the square region of tiles [t0, T) x [t0, T), processed by gridDim.x CTAs (one per SM, fewer
-// than the SM count so that the panel stream keeps a few SMs for itself); the TMA producer runs
-// ahead across tile boundaries, so there is no pipeline refill between tiles.
-// ------------------------------------------------------------------------------------------
-struct SyrkPersistParams {
-    double* C;
-    int64_t ld;
-    int t0, T;          // region of tiles
-    int kcol0, nk;
-};
-
-__device__ __forceinline__ void lower_tile(int t, int& i, int& j) {     // t -> (i, j), j <= i, row-major
-    int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-    while ((r + 1) * (r + 2) / 2 <= t) ++r;
-    while (r * (r + 1) / 2 > t) --r;
-    i = r; j = t - r * (r + 1) / 2;
-}
-
-__global__ void __launch_bounds__(SW_THREADS, 1)
-syrk_persist_kernel(const __grid_constant__ CUtensorMap tmL, SyrkPersistParams p) {
-    extern __shared__ __align__(128) unsigned char sw_smem[];
-    double* stage_base = reinterpret_cast<double*>(sw_smem);
-    uint64_t* full = reinterpret_cast<uint64_t*>(sw_smem + SW_STAGES * SW_STAGE_BYTES + 4 * 128 * 8);
-    uint64_t* empty = full + SW_STAGES;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nt = p.T - p.t0;
-    const int ntiles = nt * (nt + 1) / 2;
-
-    if (tid == 0) {
-        for (int s = 0; s < SW_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    __syncthreads();
-
-    if (warp == 8) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-                int i, j;
-                lower_tile(t, i, j);
-                const int m0 = (p.t0 + i) * 128, n0 = (p.t0 + j) * 128;
-                for (int kt = 0; kt < p.nk; ++kt) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], SW_STAGE_BYTES);
-                    double* sa = stage_base + (size_t)stage * (2 * SW_OPER_DOUBLES);
-                    double* sb = sa + SW_OPER_DOUBLES;
-                    const int k0 = p.kcol0 + kt * 16;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        tma_load_2d(sa + q * 512, &tmL, k0 + 4 * q, m0, &full[stage]);
-                        tma_load_2d(sb + q * 512, &tmL, k0 + 4 * q, n0, &full[stage]);
-                    }
-                    if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-        return;
-    }
-
-    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
-    const int fr = lane >> 2, fk = lane & 3;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        int i, j;
-        lower_tile(t, i, j);
-        const int m0 = (p.t0 + i) * 128, n0 = (p.t0 + j) * 128;
-        double acc[4][8][2];
-#pragma unroll
-        for (int a_ = 0; a_ < 4; ++a_)
-#pragma unroll
-            for (int b_ = 0; b_ < 8; ++b_) { acc[a_][b_][0] = 0.0; acc[a_][b_][1] = 0.0; }
-        for (int kt = 0; kt < p.nk; ++kt) {
-            mbar_wait(&full[stage], phase);
-            const double* a_s = stage_base + (size_t)stage * (2 * SW_OPER_DOUBLES) + ((wm + fr) << 2) + fk;
-            const double* b_s = stage_base + (size_t)stage * (2 * SW_OPER_DOUBLES) + SW_OPER_DOUBLES + ((wn + fr) << 2) + fk;
-            double a[2][4], bb[2][8];
-#pragma unroll
-            for (int a_ = 0; a_ < 4; ++a_) a[0][a_] = a_s[a_ * 32];
-#pragma unroll
-            for (int b_ = 0; b_ < 8; ++b_) bb[0][b_] = b_s[b_ * 32];
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int cur = kk & 1, nxt = cur ^ 1;
-                if (kk < 3) {
-#pragma unroll
-                    for (int a_ = 0; a_ < 4; ++a_) a[nxt][a_] = a_s[(kk + 1) * 512 + a_ * 32];
-#pragma unroll
-                    for (int b_ = 0; b_ < 8; ++b_) bb[nxt][b_] = b_s[(kk + 1) * 512 + b_ * 32];
-                }
-#pragma unroll
-                for (int a_ = 0; a_ < 4; ++a_)
-#pragma unroll
-                    for (int b_ = 0; b_ < 8; ++b_) dmma8x8x4(acc[a_][b_][0], acc[a_][b_][1], a[cur][a_], bb[cur][b_]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
-            if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
-        }
-#pragma unroll
-        for (int a_ = 0; a_ < 4; ++a_) {
-            const int row = m0 + wm + a_ * 8 + fr;
-#pragma unroll
-            for (int b_ = 0; b_ < 8; ++b_) {
-                const int col = n0 + wn + b_ * 8 + 2 * fk;
-                double2* dst = reinterpret_cast<double2*>(p.C + (int64_t)row * p.ld + col);
-                double2 o = *dst;
-                o.x -= acc[a_][b_][0];
-                o.y -= acc[a_][b_][1];
-                *dst = o;
-            }
-        }
-    }
-}
-
 }  // namespace abo
