@@ -519,3 +519,37 @@ def test_fill_distance_and_lengthscale_bounds(abo):
     d2 = abo.ContinuousDomain([0.0, 0.0], [1.0, 1.0])
     h = abo.monte_carlo_fill_distance(g, d2, n_samples=20000, rng=np.random.default_rng(2))
     assert abs(h - math.sqrt(2) * 0.25) < 1e-2
+
+
+# ---- the CUDA path against the committed golden fixture and a 50-digit arbiter ----------------
+def test_gpu_against_golden_fixture(abo):
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "known_answers.json")))
+    gp = abo.update(abo.StandardGP(abo.SqExponentialKernel(), 0.1), [0.0, 0.5, 1.0], [0.0, 0.25, 1.0])
+    assert abs(abo.posterior_mean(gp, [0.25])[0] - g["G1"]["mean"]) < 1e-10
+    assert abs(abo.posterior_var(gp, [0.25])[0] - g["G1"]["var"]) < 1e-10
+    assert abs(abo.nlml(abo.StandardGP(abo.SqExponentialKernel(), 0.1), [0.0, 0.0], [0.0, 0.5, 1.0], [0.0, 0.25, 1.0])
+               - g["G2"]["nlml"]) < 1e-10
+    gp3 = abo.update(abo.StandardGP(abo.SqExponentialKernel(), 0.1), [0.0, 0.5, 1.0], [2.0, 1.0, 0.5])
+    assert abs(abo.ExpectedImprovement(0.01, 0.5)(gp3, [0.25])[0] - g["G3"]["EI"]) < 1e-9 * g["G3"]["EI"]
+    assert abs(abo.ProbabilityImprovement(0.01, 0.5)(gp3, [0.25])[0] - g["G3"]["PI"]) < 1e-9 * g["G3"]["PI"]
+    assert abs(abo.UpperConfidenceBound(2.0)(gp3, [0.25])[0] - g["G3"]["UCB_beta2"]) < 1e-10
+
+
+@pytest.mark.parametrize("noise", [1e-4, 1e-8, 1e-10])
+def test_ill_conditioned_against_mpmath_arbiter(abo, orc, noise):
+    """with cond(K) up to ~1e9 two valid FP64 evaluations differ by more than 1e-9, so the
+    GPU is judged against 50-digit truth: its error may not exceed max(1e-9*scale, 4 x the oracle's)."""
+    rng = np.random.default_rng(12)
+    X = rng.random((40, 2)); y = np.sin(4 * X[:, 0]) * np.cos(3 * X[:, 1])
+    Xc = rng.random((25, 2))
+    gp = abo.update(abo.StandardGP(make_kernel(abo, 0, 1.0 / 0.6, 1.0), noise), X, y)
+    post = orc.fit_standard(X, y, 0, 1.0 / 0.6, 1.0, noise)
+    mu_o, var_o = orc.posterior_mean_var(post, Xc)
+    mu_t, var_t = orc.mp_posterior_standard(X, y, 0, 1.0 / 0.6, 1.0, noise, 0.0, Xc)
+    mu_t = np.array([float(v) for v in mu_t]); var_t = np.array([float(v) for v in var_t])
+    mu = abo.posterior_mean(gp, Xc); var = abo.posterior_var(gp, Xc)
+    e_gpu_m, e_orc_m = np.max(np.abs(mu - mu_t)), np.max(np.abs(mu_o - mu_t))
+    e_gpu_v, e_orc_v = np.max(np.abs(var - var_t)), np.max(np.abs(var_o - var_t))
+    assert e_gpu_m <= max(1e-9, 4 * e_orc_m), (e_gpu_m, e_orc_m)
+    assert e_gpu_v <= max(1e-9, 4 * e_orc_v), (e_gpu_v, e_orc_v)

@@ -272,3 +272,27 @@ def test_configs_are_deterministic(name, kw):
     for k in a:
         if isinstance(a[k], np.ndarray):
             assert np.array_equal(a[k], b[k])
+
+
+# ---- committed golden fixture (tests/golden/known_answers.json, generated by make_known_answers.py)
+def _golden():
+    import json, os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "known_answers.json")))
+
+
+def test_oracle_against_golden_fixture():
+    g = _golden()
+    xs = np.array([[0.0], [0.5], [1.0]])
+    post = orc.fit_standard(xs, [0.0, 0.25, 1.0], orc.SE, 1.0, 1.0, 0.1)
+    mu, var = orc.posterior_mean_var(post, [[0.25]])
+    assert abs(mu[0] - g["G1"]["mean"]) < 1e-14 and abs(var[0] - g["G1"]["var"]) < 1e-14
+    assert abs(orc.nlml(xs, [0.0, 0.25, 1.0], orc.SE, 0.0, 0.0, 0.1) - g["G2"]["nlml"]) < 1e-13
+    post = orc.fit_standard(xs, [2.0, 1.0, 0.5], orc.SE, 1.0, 1.0, 0.1)
+    mu, var = orc.posterior_mean_var(post, [[0.25]])
+    assert abs(orc.expected_improvement(mu, var, 0.01, 0.5)[0] - g["G3"]["EI"]) < 1e-9 * g["G3"]["EI"]
+    assert abs(orc.probability_improvement(mu, var, 0.01, 0.5)[0] - g["G3"]["PI"]) < 1e-9 * g["G3"]["PI"]
+    assert abs(orc.upper_confidence_bound(mu, var, 2.0)[0] - g["G3"]["UCB_beta2"]) < 1e-13
+    K = orc.grad_kernelmatrix(orc.SE, 1.0, 1.0, [[0.5, 0.5]], [[0.6, 0.6]])
+    assert abs(K[0, 0] - g["G4"]["k"]) < 1e-15 and abs(K[0, 1] - g["G4"]["dk_dy"]) < 1e-15
+    assert abs(K[1, 0] - g["G4"]["dk_dx"]) < 1e-15 and abs(K[1, 1] - g["G4"]["d2k_diag"]) < 1e-15
+    assert abs(K[1, 2] - g["G4"]["d2k_offdiag"]) < 1e-15
