@@ -78,6 +78,8 @@ extern "C" int32_t abo_ctx_create(int32_t device, abo_ctx** out) {
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));    // main / panel stream
     CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));   // look-ahead trailing updates
+    CU(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_hi));   // bulk half of the panel chain
+    for (int q = 0; q < 3; ++q) CU(cudaEventCreateWithFlags(&c->ev_p[q], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
     for (int q = 0; q < 2; ++q) {
@@ -103,6 +105,8 @@ extern "C" int32_t abo_ctx_destroy(abo_ctx* c) {
     for (int q = 0; q < 2; ++q) { cudaEventDestroy(c->ev_ks[q]); cudaEventDestroy(c->ev_sw[q]); }
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->stream2);
+    cudaStreamDestroy(c->stream3);
+    for (int q = 0; q < 3; ++q) cudaEventDestroy(c->ev_p[q]);
     delete c;
     return ABO_OK;
 }
@@ -310,6 +314,9 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
     CU(cudaEventRecord(c->ev_a, sp));                 // su must see everything enqueued on sp so far
     CU(cudaStreamWaitEvent(su, c->ev_a, 0));
     bool rest_pending = false;
+    bool s3_pending = false;
+    cudaStream_t s3 = c->stream3;
+    static const bool split = getenv("ABO_POTRF_NOSPLIT") == nullptr;
     static const bool trace = getenv("ABO_POTRF_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;           // per outer block: start, panel done, U_next done (sp), U_rest start, done (su)
     auto mark = [&](cudaStream_t s_) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); tev.push_back(e); } };
@@ -329,26 +336,54 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
             double* Dj = Dinv + (int64_t)jp * NB * NB;
             CU(launch_pdl(potf2_ws_kernel, dim3(1), dim3(512), PW_SMEM_BYTES, sp, pdl, Ajj, ld, (int64_t)0, Dj, (int64_t)0, info, jp * NB));
             KL(c);
+            if (s3_pending) { CU(cudaStreamWaitEvent(sp, c->ev_p[2], 0)); s3_pending = false; }   // bulk of the previous panel
             const int rem = (T - jp - 1) * NB;
             if (rem <= 0) break;
             double* P = Ajj + (int64_t)NB * ld;
-            GemmParams g{};
+            const int ncol = (je - jp - 1) * NB;       // remaining columns of this outer block
+            auto gemm_panel = [&](const GemmParams& q, cudaStream_t s_, bool pdl_) -> int {
+                if (q.M <= 0 || q.N <= 0) return ABO_OK;
+                if (q.M >= big_rem) CU(launch_pdl(gemm_small_kernel<64, 8>, dim3(q.N / BN, q.M / 64, 1), dim3(256), GemmS<64, 8>::SMEM_BYTES, s_, pdl_, q));
+                else CU(launch_pdl(gemm_small_kernel<32, 8>, dim3(q.N / BN, q.M / 32, 1), dim3(256), GemmS<32, 8>::SMEM_BYTES, s_, pdl_, q));
+                KL(c);
+                return ABO_OK;
+            };
+            GemmParams g{};                            // TRSM as GEMM: L_ij = A_ij * inv(L_jj)^T, in place
             g.A = P; g.lda = ld; g.B = Dj; g.ldb = NB; g.C = P; g.ldc = ld;
             g.M = rem; g.N = NB; g.K = NB; g.alpha = 1.0; g.beta = 0.0; g.flags = 0;
-            if (rem >= big_rem) CU(launch_pdl(gemm_small_kernel<64, 8>, dim3(g.N / BN, g.M / 64, 1), dim3(256), GemmS<64, 8>::SMEM_BYTES, sp, pdl, g));
-            else CU(launch_pdl(gemm_small_kernel<32, 8>, dim3(g.N / BN, g.M / 32, 1), dim3(256), GemmS<32, 8>::SMEM_BYTES, sp, pdl, g));
-            KL(c);
-            const int ncol = (je - jp - 1) * NB;       // remaining columns of this outer block
-            if (ncol > 0) {
-                GemmParams s{};
-                s.A = P; s.lda = ld; s.B = P; s.ldb = ld;
-                s.C = Ajj + (int64_t)NB * (ld + 1); s.ldc = ld;
-                s.M = rem; s.N = ncol; s.K = NB; s.alpha = -1.0; s.beta = 1.0; s.flags = LOWER_ONLY;
-                if (rem >= big_rem) CU(launch_pdl(gemm_small_kernel<64, 8>, dim3(s.N / BN, s.M / 64, 1), dim3(256), GemmS<64, 8>::SMEM_BYTES, sp, pdl, s));
-                else CU(launch_pdl(gemm_small_kernel<32, 8>, dim3(s.N / BN, s.M / 32, 1), dim3(256), GemmS<32, 8>::SMEM_BYTES, sp, pdl, s));
-                KL(c);
+            GemmParams s{};                            // in-block SYRK: A_22 -= L_21 L_21^T (columns of this outer block)
+            s.A = P; s.lda = ld; s.B = P; s.ldb = ld;
+            s.C = Ajj + (int64_t)NB * (ld + 1); s.ldc = ld;
+            s.M = rem; s.N = ncol; s.K = NB; s.alpha = -1.0; s.beta = 1.0; s.flags = LOWER_ONLY;
+            int rc2;
+            if (!split || ncol <= 0 || rem <= NB) {
+                if ((rc2 = gemm_panel(g, sp, pdl))) return rc2;
+                if ((rc2 = gemm_panel(s, sp, pdl))) return rc2;
+            } else {
+                // split panel chain: only the next diagonal tile is on the critical path of the next
+                // potf2; the bulk of the TRSM / in-block SYRK runs on a third stream concurrently with it
+                CU(cudaEventRecord(c->ev_p[0], sp));                       // potf2(jp) done
+                GemmParams g1 = g; g1.M = NB;                              // tile row jp+1
+                if ((rc2 = gemm_panel(g1, sp, false))) return rc2;
+                CU(cudaEventRecord(c->ev_p[1], sp));                       // L[jp+1, jp] final
+                GemmParams s1 = s; s1.M = NB; s1.N = NB; s1.flags = 0;     // diagonal tile (jp+1, jp+1)
+                if ((rc2 = gemm_panel(s1, sp, false))) return rc2;
+                CU(cudaStreamWaitEvent(s3, c->ev_p[0], 0));
+                GemmParams g2 = g; g2.A = P + (int64_t)NB * ld; g2.C = P + (int64_t)NB * ld; g2.M = rem - NB;
+                if ((rc2 = gemm_panel(g2, s3, false))) return rc2;         // remaining rows of the TRSM
+                CU(cudaStreamWaitEvent(s3, c->ev_p[1], 0));
+                GemmParams s2 = s;                                         // remaining tiles: rows from tile jp+2
+                s2.A = P + (int64_t)NB * ld; s2.C = s.C + (int64_t)NB * ld; s2.M = rem - NB; s2.lower_shift = NB;
+                if ((rc2 = gemm_panel(s2, s3, false))) return rc2;
+                CU(cudaEventRecord(c->ev_p[2], s3));
+                s3_pending = true;
+            }
+            if (s3_pending && jp + 1 < je) {
+                // the next panel's potf2 only needs the diagonal tile; its TRSM needs everything: make the
+                // panel stream wait for the bulk right after that potf2 has been enqueued (below)
             }
         }
+        if (s3_pending) { CU(cudaStreamWaitEvent(sp, c->ev_p[2], 0)); s3_pending = false; }
         mark(sp);
         if (je >= T) break;
         SyrkParams u;

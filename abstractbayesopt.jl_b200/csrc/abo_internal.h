@@ -38,7 +38,8 @@ struct WsBuf { void* ptr = nullptr; size_t bytes = 0; };
 struct abo_ctx {
     int device = 0;
     int sms = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
+    cudaEvent_t ev_p[3] = {nullptr, nullptr, nullptr};            // panel-chain split of the Cholesky
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     cudaEvent_t ev_ks[2] = {nullptr, nullptr}, ev_sw[2] = {nullptr, nullptr};   // K* builder / contraction ping-pong
     WsBuf ws[WS_COUNT];

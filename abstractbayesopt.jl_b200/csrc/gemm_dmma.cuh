@@ -41,6 +41,7 @@ struct GemmParams {
     int M, N, K;                         // multiples of 128 / 128 / 16
     double alpha, beta;
     int flags;
+    int lower_shift;                     // LOWER_ONLY keeps tiles with n0 <= m0 + lower_shift (C starts lower_shift rows below the diagonal)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 2) gemm_small_kernel(Ge
     const int wm = (warp % S::WM) * 32, wn = (warp / S::WM) * S::WNC;
     const int m0 = blockIdx.y * BMT, n0 = blockIdx.x * BN;
     pdl_launch_dependents();
-    if ((p.flags & LOWER_ONLY) && n0 > m0) return;
+    if ((p.flags & LOWER_ONLY) && n0 > m0 + p.lower_shift) return;
     const double* A = p.A + (int64_t)blockIdx.z * p.strideA;
     const double* B = p.B + (int64_t)blockIdx.z * p.strideB;
     const int nk = p.K / BK;
