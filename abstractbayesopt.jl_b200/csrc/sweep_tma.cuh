@@ -192,8 +192,8 @@ sweep_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // small kernels in between tiles.  A and B are both K-contiguous row panels of the SAME
 // row-major matrix, hence one tensor map.
 // ------------------------------------------------------------------------------------------
-// 4 stages (131 KB): leaves room on the SM for a 128-thread / 80 KB panel CTA of the other stream
-constexpr int SY_STAGES = 4;
+// same ring depth as the sweep kernel
+constexpr int SY_STAGES = 5;
 constexpr int SY_SMEM_BYTES = SY_STAGES * SW_STAGE_BYTES + 4 * 128 * 8 + 2 * SY_STAGES * 8 + 128;
 
 struct SyrkParams {

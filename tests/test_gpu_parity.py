@@ -553,3 +553,27 @@ def test_ill_conditioned_against_mpmath_arbiter(abo, orc, noise):
     e_gpu_v, e_orc_v = np.max(np.abs(var - var_t)), np.max(np.abs(var_o - var_t))
     assert e_gpu_m <= max(1e-9, 4 * e_orc_m), (e_gpu_m, e_orc_m)
     assert e_gpu_v <= max(1e-9, 4 * e_orc_v), (e_gpu_v, e_orc_v)
+
+
+def test_determinism_and_instrumentation(abo, orc):
+    """Replicas must be bit-identical (redundant per-rank fits instead of a broadcast are only
+    valid if the kernels are deterministic): two independent fits and sweeps give the same bits."""
+    c = orc.make_config("C4", n=900, m=6000, d=20)
+    k = make_kernel(abo, c["kind"], c["inv_ls"], c["scale"])
+    g1 = abo.update(abo.StandardGP(k, c["noise"]), c["X"], c["y"])
+    g2 = abo.update(abo.StandardGP(k, c["noise"]), c["X"], c["y"])
+    assert np.array_equal(g1.gpx.factor(0), g2.gpx.factor(0)) and np.array_equal(g1.gpx.factor(1), g2.gpx.factor(1))
+    acq = abo.UpperConfidenceBound(2.0)
+    ctx = abo.default_context()
+    n0 = ctx.launch_count()
+    s1, t1, _ = acq.topk(g1, c["Xc"], 50)
+    assert ctx.launch_count() > n0                                   # our kernels ran (no fallback exists)
+    s2, t2, _ = acq.topk(g2, c["Xc"], 50)
+    assert np.array_equal(s1, s2) and np.array_equal(t1, t2)
+    ctx.profile(True); acq(g1, c["Xc"]); ms, cnt = ctx.profile_read(); ctx.profile(False)
+    assert cnt[0] == cnt[1] == cnt[2] >= 1 and ms[1] > 0
+    # clone is a deep copy: appending to the clone leaves the original untouched
+    g3 = abo.copy(g1)
+    g4 = abo.update(g3, np.vstack([c["X"], c["Xc"][:1]]), np.concatenate([c["y"], [0.3]]))
+    assert g4.gpx.n() == 901 and g1.gpx.n() == 900 and g3.gpx.n() == 900
+    assert np.array_equal(acq(g1, c["Xc"][:500]), s1[:500])
