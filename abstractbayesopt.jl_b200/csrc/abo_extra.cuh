@@ -114,8 +114,8 @@ extern "C" int32_t abo_gp_append(abo_gp* g, const double* x, const double* y, in
     const double l = std::sqrt(piv);
     // r = Linv^T w over rows 0..n-1
     const int nchunks = (int)((n + TRMVT_ROWS - 1) / TRMVT_ROWS);
-    double* part;
-    if ((rc = ws_get(c, WS_VEC_PART, sizeof(double) * (size_t)nchunks * n, (void**)&part))) return rc;
+    double* part;                              // sized by the padded dimension: no re-allocation as n grows
+    if ((rc = ws_get(c, WS_VEC_PART, sizeof(double) * (size_t)(Np / TRMVT_ROWS + 2) * (Np + NB), (void**)&part))) return rc;
     {
         dim3 grid((unsigned)((n + 127) / 128), nchunks, 1);
         trmvT_lower_partial_kernel<<<grid, 128, 0, st>>>(g->dLinv, g->ld, n, w, part, 0, 0, 0);

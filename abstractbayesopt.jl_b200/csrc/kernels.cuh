@@ -412,7 +412,8 @@ __global__ void trmv_lower_kernel(const double* __restrict__ T, int64_t ld, int6
     const double* row = T + (int64_t)blockIdx.y * strideT + r * ld;
     const double* vv = v + (int64_t)blockIdx.y * strideV;
     double s = 0.0;
-    for (int64_t k = lane; k <= r; k += 32) s = fma(row[k], vv[k], s);
+#pragma unroll 8
+    for (int64_t k = lane; k <= r; k += 32) s = fma(row[k], vv[k], s);      // 8 loads in flight per lane
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) out[(int64_t)blockIdx.y * strideV + r] = s;
@@ -430,6 +431,7 @@ __global__ void trmvT_lower_partial_kernel(const double* __restrict__ T, int64_t
     const double* vv = v + (int64_t)blockIdx.z * strideV;
     int64_t i1 = i0 + TRMVT_ROWS; if (i1 > N) i1 = N;
     double s = 0.0;
+#pragma unroll 8
     for (int64_t i = (i0 > j ? i0 : j); i < i1; ++i) s = fma(Tb[i * ld + j], vv[i], s);
     part[(int64_t)blockIdx.z * strideP + (int64_t)blockIdx.y * N + j] = s;
 }
