@@ -302,7 +302,9 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
     static const int OB_env = getenv("ABO_POTRF_OB") ? atoi(getenv("ABO_POTRF_OB")) : 3;
     static const bool one_stream = getenv("ABO_POTRF_1STREAM") != nullptr;
     static const bool pdl_on = getenv("ABO_NO_PDL") == nullptr;
+    static const int pdl_tiles = getenv("ABO_POTRF_PDLTILES") ? atoi(getenv("ABO_POTRF_PDLTILES")) : 40;
     static const bool ramp = getenv("ABO_POTRF_NORAMP") == nullptr;
+    static const int small_next = getenv("ABO_POTRF_SMALLNEXT") ? atoi(getenv("ABO_POTRF_SMALLNEXT")) : 60;
     // panel GEMMs: 64-row tiles while the panel is tall (throughput), 32-row tiles once it is short (latency)
     static const int big_rem = getenv("ABO_POTRF_BIGREM") ? atoi(getenv("ABO_POTRF_BIGREM")) : 4096;
     const int OB = std::max(1, OB_env);
@@ -328,7 +330,7 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
         je = std::min(Jb + (ramp ? std::min(step + 1, OB) : OB), T);
         // PDL only once the trailing matrix is small: early-resident dependents would otherwise take
         // shared memory away from the big trailing-update CTAs of the second stream
-        const bool pdl = pdl_on && (T - Jb) <= 12;
+        const bool pdl = pdl_on && (T - Jb) <= pdl_tiles;
         // ---- panel block: tile columns [Jb, je)
         mark(sp);
         for (int jp = Jb; jp < je; ++jp) {
@@ -362,16 +364,16 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
             } else {
                 // split panel chain: only the next diagonal tile is on the critical path of the next
                 // potf2; the bulk of the TRSM / in-block SYRK runs on a third stream concurrently with it
-                CU(cudaEventRecord(c->ev_p[0], sp));                       // potf2(jp) done
+                // (the three critical kernels stay back to back on the panel stream so that PDL applies;
+                //  the bulk stream picks up after them — it has a full potf2 of slack)
                 GemmParams g1 = g; g1.M = NB;                              // tile row jp+1
-                if ((rc2 = gemm_panel(g1, sp, false))) return rc2;
-                CU(cudaEventRecord(c->ev_p[1], sp));                       // L[jp+1, jp] final
+                if ((rc2 = gemm_panel(g1, sp, pdl))) return rc2;
                 GemmParams s1 = s; s1.M = NB; s1.N = NB; s1.flags = 0;     // diagonal tile (jp+1, jp+1)
-                if ((rc2 = gemm_panel(s1, sp, false))) return rc2;
-                CU(cudaStreamWaitEvent(s3, c->ev_p[0], 0));
+                if ((rc2 = gemm_panel(s1, sp, pdl))) return rc2;
+                CU(cudaEventRecord(c->ev_p[1], sp));                       // potf2(jp), L[jp+1, jp] final
+                CU(cudaStreamWaitEvent(s3, c->ev_p[1], 0));
                 GemmParams g2 = g; g2.A = P + (int64_t)NB * ld; g2.C = P + (int64_t)NB * ld; g2.M = rem - NB;
                 if ((rc2 = gemm_panel(g2, s3, false))) return rc2;         // remaining rows of the TRSM
-                CU(cudaStreamWaitEvent(s3, c->ev_p[1], 0));
                 GemmParams s2 = s;                                         // remaining tiles: rows from tile jp+2
                 s2.A = P + (int64_t)NB * ld; s2.C = s.C + (int64_t)NB * ld; s2.M = rem - NB; s2.lower_shift = NB;
                 if ((rc2 = gemm_panel(s2, s3, false))) return rc2;
@@ -402,8 +404,21 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
         // ---- U_next(b) on the panel stream: the next block's columns; they were last touched by
         //      U_rest(b-1), so wait for it
         if (rest_pending) CU(cudaStreamWaitEvent(sp, c->ev_b, 0));
-        u.row_t0 = je; u.col_t0 = je;
-        CU(launch_pdl(syrk_tma_kernel, dim3(jn - je, T - je), dim3(SW_THREADS), SY_SMEM_BYTES, sp, pdl && !rest_pending, tmL, u));
+        if ((T - je) * (jn - je) <= small_next) {
+            // few tiles: one 128x128xK tile per CTA would leave most SMs idle for a full tile time
+            // (~55 us); 32-row tiles finish the slab in ~1/3 of that
+            GemmParams nx{};
+            nx.A = A + (int64_t)je * NB * ld + (int64_t)Jb * NB; nx.lda = ld;
+            nx.B = nx.A; nx.ldb = ld;
+            nx.C = A + (int64_t)je * NB * (ld + 1); nx.ldc = ld;
+            nx.M = (T - je) * NB; nx.N = (jn - je) * NB; nx.K = (je - Jb) * NB;
+            nx.alpha = -1.0; nx.beta = 1.0; nx.flags = LOWER_ONLY;
+            CU(launch_pdl(gemm_small_kernel<32, 8>, dim3(nx.N / BN, nx.M / 32, 1), dim3(256), GemmS<32, 8>::SMEM_BYTES, sp,
+                          pdl && !rest_pending, nx));
+        } else {
+            u.row_t0 = je; u.col_t0 = je;
+            CU(launch_pdl(syrk_tma_kernel, dim3(jn - je, T - je), dim3(SW_THREADS), SY_SMEM_BYTES, sp, pdl && !rest_pending, tmL, u));
+        }
         KL(c);
         mark(sp);
         if (jn < T) { CU(cudaEventRecord(c->ev_b, su)); rest_pending = true; }

@@ -181,11 +181,14 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
     pdl_wait();
     const bool stamp = (tid == 0 && blockIdx.x == 0);
     if (stamp) g_potf2_clk[0] = clock64();
-    for (int e = tid; e < 128 * 128; e += 512) {
-        int r = e >> 7, c = e & 127;
-        sL[r * POTF2_LD + c] = A[(int64_t)r * ld + c];
+    // warps 1..15 stage the block in shared memory; warp 0 takes the first diagonal block D_0 straight
+    // from global memory into registers and factors it meanwhile (its result is what everybody waits for)
+    if (warp > 0) {
+        for (int e = tid - 32; e < 128 * 128; e += 480) {
+            int r = e >> 7, c = e & 127;
+            if (r >= 32 || c >= 32) sL[r * POTF2_LD + c] = A[(int64_t)r * ld + c];
+        }
     }
-    __syncthreads();
     if (stamp) g_potf2_clk[1] = clock64();
 
     if (warp < 8) {
@@ -194,8 +197,13 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
             const int c0 = sp * 32, c1 = c0 + 32;
             if (warp == 0) {
                 double a[32];
+                if (sp == 0) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) a[c] = sL[(c0 + lane) * POTF2_LD + c0 + c];
+                    for (int c = 0; c < 32; ++c) a[c] = A[(int64_t)lane * ld + c];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) a[c] = sL[(c0 + lane) * POTF2_LD + c0 + c];
+                }
                 int failcol = -1;
                 double d = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
@@ -232,10 +240,20 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
                     }
                 }
             }
-            bar_named(1, 256);                             // D_sp is final for the factor group ...
-            asm volatile("bar.arrive %0, 512;\n" ::"r"(4 + sp) : "memory");   // ... and signalled to the inverse group (never waits for it)
+            if (sp == 0) {
+                __syncthreads();                           // block staged by warps 1..15 AND D_0 final
+            } else {
+                bar_named(1, 256);                         // D_sp is final for the factor group ...
+                asm volatile("bar.arrive %0, 512;\n" ::"r"(4 + sp) : "memory");   // ... and signalled to the inverse group (never waits for it)
+            }
             if (s_fail) break;
-            if (c1 >= 128) break;
+            if (c1 >= 128) {                               // last column block: its rows are final now
+                for (int e = tid; e < 128 * 32; e += 256) {
+                    const int r = e >> 5, cc = c0 + (e & 31);
+                    A[(int64_t)r * ld + cc] = (cc <= r) ? sL[r * POTF2_LD + cc] : 0.0;
+                }
+                break;
+            }
             {
                 const int r = c1 + (warp - 1) * 32 + lane;
                 if (warp >= 1 && r < 128) {
@@ -259,7 +277,13 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
                 }
             }
             bar_named(1, 256);
-            asm volatile("bar.arrive %0, 512;\n" ::"r"(8 + sp) : "memory");   // rows below column block sp are final: inverse group may read them
+            for (int e = tid; e < 128 * 32; e += 256) {    // column block sp of L is final: write it back now
+                const int r = e >> 5, cc = c0 + (e & 31);
+                A[(int64_t)r * ld + cc] = (cc <= r) ? sL[r * POTF2_LD + cc] : 0.0;
+            }
+            // rows below column block sp are final AND D_sp has been written back: the inverse group may read
+            // the former and overwrite the latter (it parks X_sp,sp there)
+            asm volatile("bar.arrive %0, 512;\n" ::"r"(8 + sp) : "memory");
             const int nt = (128 - c1) / 16;
             const int ntile = nt * (nt + 1) / 2;
             for (int t = warp; t < ntile; t += 8) {
@@ -291,15 +315,7 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
             }
             bar_named(1, 256);
         }
-        if (stamp) g_potf2_clk[2] = clock64();
-        // write L back while the inverse group finishes its last round
-        if (!s_fail) {
-            for (int e = tid; e < 128 * 128; e += 256) {
-                int r = e >> 7, c = e & 127;
-                A[(int64_t)r * ld + c] = (c <= r) ? sL[r * POTF2_LD + c] : 0.0;
-            }
-        }
-        if (stamp) g_potf2_clk[3] = clock64();
+        if (stamp) { g_potf2_clk[2] = clock64(); g_potf2_clk[3] = g_potf2_clk[2]; }
     } else {
         // =============================== INVERSE GROUP ===============================
         const int it = tid - 256, iw = warp - 8;
@@ -313,15 +329,26 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
                 // ---- (ahead of the hand-off) S_st = sum_{u=t}^{s-1} L_su X_ut : strips (t, ti) of four
                 //      8x8 tiles; needs X rows < s (this group) and L_s,u<s (factor group: barrier 3)
                 bar_named(8 + s - 1, 512);
+                // X_{s-1,s-1} (still in sXs) takes the place of D_{s-1} in sL; the strictly-upper 32-blocks of
+                // sL are free and hold the off-diagonal X_ut at block position (t, u): everything the S
+                // products need is then in shared memory
+                for (int e = it; e < 32 * 32; e += 256) {
+                    const int r = e >> 5, cc = e & 31;
+                    sL[(c0 - 32 + r) * POTF2_LD + c0 - 32 + cc] = sXs[r * PW_XLD + cc];
+                }
+                bar_named(2, 256);
                 for (int g = iw; g < 4 * s; g += 8) {
                     const int t = g >> 2, ti = g & 3;
                     double cc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
                     const double* arow = sL + (c0 + ti * 8 + fr) * POTF2_LD + fk;
-                    for (int k = 32 * t; k < c0; k += 4) {
-                        const double a = arow[k];
-                        const double* brow = Di + (k + fk) * 128 + 32 * t + fr;
+                    for (int kq = 32 * t; kq < c0; kq += 4) {
+                        const double a = arow[kq];
+                        // X_ut[k][n], u = kq / 32: block (t, t) on the diagonal for u == t, else upper block (t, u)
+                        const int u = kq >> 5;
+                        const double* brow = (u == t) ? sL + (kq + fk) * POTF2_LD + 32 * t + fr
+                                                      : sL + (32 * t + (kq & 31) + fk) * POTF2_LD + 32 * u + fr;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) dmma8x8x4(cc[q][0], cc[q][1], a, brow[q * 8]);   // written by this CTA (same SM, same L1)
+                        for (int q = 0; q < 4; ++q) dmma8x8x4(cc[q][0], cc[q][1], a, brow[q * 8]);
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -330,7 +357,11 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
                     }
                 }
             }
-            bar_named(4 + s, 512);                         // hand-off: D_s is final (factor group only arrives)
+            const bool istamp = (it == 0 && blockIdx.x == 0 && s == 3);
+            if (istamp) g_potf2_clk[11] = clock64();
+            if (s == 0) __syncthreads();                   // block staged and D_0 final
+            else bar_named(4 + s, 512);                    // hand-off: D_s is final (factor group only arrives)
+            if (istamp) g_potf2_clk[12] = clock64();
             if (s_fail) break;
             // ---- X_ss = inv(D_s) by ONE warp, no barriers: lane = column c of the inverse, right-looking
             //      substitution  x_j = acc_j / L_jj ; acc_i -= L_ij x_j (i > j)  with L broadcast from sL.
@@ -353,6 +384,7 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
                 for (int i = 0; i < 32; ++i) sXs[i * PW_XLD + lane] = acc[i];
             }
             bar_named(2, 256);
+            if (istamp) g_potf2_clk[13] = clock64();
             for (int e = it; e < 32 * 32; e += 256) {          // X_ss -> global (upper part is zero)
                 int r = e >> 5, c = e & 31;
                 Di[(c0 + r) * 128 + c0 + c] = sXs[r * PW_XLD + c];
@@ -373,19 +405,18 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
                     for (int q = 0; q < 4; ++q) {
                         double* dst = Di + (c0 + ti * 8 + fr) * 128 + 32 * t + q * 8 + 2 * fk;
                         dst[0] = -cc[q][0]; dst[1] = -cc[q][1];
+                        double* dsm = sL + (32 * t + ti * 8 + fr) * POTF2_LD + c0 + q * 8 + 2 * fk;   // upper block (t, s)
+                        dsm[0] = -cc[q][0]; dsm[1] = -cc[q][1];
                     }
                 }
             }
             bar_named(2, 256);                               // sXs / sS free for the next round
+            if (istamp) g_potf2_clk[14] = clock64();
         }
     }
     __syncthreads();
-    if (s_fail) {                                            // harmless identity as the inverse
+    if (s_fail) {                                            // harmless identity as the inverse; A stays as it is
         for (int e = tid; e < 128 * 128; e += 512) Di[e] = ((e >> 7) == (e & 127)) ? 1.0 : 0.0;
-        for (int e = tid; e < 128 * 128; e += 512) {
-            int r = e >> 7, c = e & 127;
-            A[(int64_t)r * ld + c] = (c <= r) ? sL[r * POTF2_LD + c] : 0.0;
-        }
     }
     if (stamp) g_potf2_clk[6] = clock64();
 }

@@ -22,5 +22,5 @@ for n in sizes:
     L = torch.tril(A)
     err = (torch.linalg.norm(L @ L.T - K0) / torch.linalg.norm(K0)).item()
     ck = ctx.potf2_clocks(); names = ["load", "factor", "storeL", "inv0", "invL", "storeD"]
-    print("   potf2 phases (cycles):", {names[i]: ck[i + 1] - ck[i] for i in range(6)}, "total", ck[6] - ck[0], "| sub-panel 0: diag", ck[8] - ck[1], "trsm", ck[9] - ck[8], "update", ck[10] - ck[9])
+    print("   potf2 phases (cycles):", {names[i]: ck[i + 1] - ck[i] for i in range(6)}, "total", ck[6] - ck[0], "| sub-panel 0: diag", ck[8] - ck[1], "trsm", ck[9] - ck[8], "update", ck[10] - ck[9], "| inverse round 3: early-S done -> D_3 ready", ck[12] - ck[11], "X_33", ck[13] - ck[12], "multiply+store", ck[14] - ck[13], "| F done at", ck[2] - ck[0], "I done at", ck[14] - ck[0])
     print(f"n={n} potrf {best:.3f} ms  {fl / best / 1e9:.2f} TFLOP/s  relres={err:.2e}", flush=True)
