@@ -52,6 +52,9 @@ static int configure_kernels() {
     CU(cudaFuncSetAttribute(fill_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 96 * 8));
     CU(cudaFuncSetAttribute(potf2_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_BYTES));
     CU(cudaFuncSetAttribute(sweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(gemm_ws_kernel<KC, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(gemm_ws_kernel<MC, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(gemm_ws_kernel<KC, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
     CU(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
     return ABO_OK;
 }
@@ -444,6 +447,9 @@ int trtri_blocked(abo_ctx* c, const double* L, double* Linv, double* W, int64_t 
                   const double* Dinv, int64_t strideD, int batch) {
     const int T = (int)(Npad / NB);
     cudaStream_t st = c->stream;
+    // the warp-specialised kernel pays off once the k-loops are long; small / batched problems keep the
+    // lighter barrier-synchronised kernel
+    const bool use_ws = getenv("ABO_GEMM_V1") == nullptr && Npad >= 4096;
     place_diag_kernel<<<dim3(T, batch), 256, 0, st>>>(Dinv, Linv, ld, strideD, strideM);
     KL(c);
     for (int b = 1; b < T; b <<= 1) {
@@ -479,7 +485,7 @@ int trtri_blocked(abo_ctx* c, const double* L, double* Linv, double* W, int64_t 
                         g.M = rr * NB; g.N = b * NB; g.K = rr * NB; g.alpha = -1.0; g.flags = KHI_M;
                     }
                     g.lda = g.ldb = g.ldc = ld; g.strideA = g.strideB = g.strideC = zs; g.beta = 0.0;
-                    CU((launch_gemm<KC, MC, EPI_STORE>(g, zb, st)));
+                    if (use_ws) CU((launch_gemm_ws<KC, MC>(g, zb, st))); else CU((launch_gemm<KC, MC, EPI_STORE>(g, zb, st)));
                     KL(c);
                 }
             }

@@ -210,7 +210,8 @@ extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, i
             q.A = Linv; q.B = Linv; q.C = W;
             q.lda = q.ldb = q.ldc = Npad; q.strideA = q.strideB = q.strideC = Npad * Npad;
             q.M = q.N = q.K = (int)Npad; q.alpha = 1.0; q.beta = 0.0; q.flags = KLO_M | LOWER_ONLY;
-            CU((launch_gemm<MC, MC, EPI_STORE>(q, nb, st)));
+            if (Npad >= 4096) CU((launch_gemm_ws<MC, MC>(q, nb, st)));
+            else CU((launch_gemm<MC, MC, EPI_STORE>(q, nb, st)));
             KL(c);
             nlml_grad_tile_kernel<<<dim3(T, T, nb), 256, 0, st>>>(spec, bt, Xb, ldx, N, W, Npad, Npad * Npad, alpha, Npad, tpart);
             KL(c);

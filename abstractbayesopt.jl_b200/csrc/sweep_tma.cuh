@@ -298,3 +298,144 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmL, SyrkParams p) {
 
 
 }  // namespace abo
+
+// ------------------------------------------------------------------------------------------
+// gemm_ws_kernel<LA, LB> — warp-specialised general tile GEMM  C = alpha * A op(B) + beta * C  for the
+// operand layouts TMA boxes cannot stage conflict-free (MN-contiguous operands of the triangular
+// inverse and of L^-T L^-1): two PRODUCER warps issue 16-byte cp.async copies into the same
+// shared-memory layouts as gemm_dmma_kernel and signal an mbarrier ring with
+// cp.async.mbarrier.arrive; eight CONSUMER warps run the DMMA inner loop of the sweep kernel with no
+// block-wide barrier.  One 128 x 128 tile per CTA; k-range flags as in gemm_dmma.cuh.
+// ------------------------------------------------------------------------------------------
+namespace abo {
+
+constexpr int WS_STAGES = 5;
+constexpr int WS_THREADS = 256 + 64;
+constexpr int WS_SMEM_BYTES = WS_STAGES * 2 * TILE_DOUBLES * (int)sizeof(double) + 2 * WS_STAGES * 8 + 64;
+
+template <int LAYOUT>
+__device__ __forceinline__ void ws_load_tile(double* s, const double* g, int64_t ld, int r0, int k0, int lane) {
+    // one warp copies a 128 x 16 operand tile: 1024 chunks of 16 bytes, 32 per lane
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) {
+        const int c = lane + 32 * q;
+        if (LAYOUT == KC) {
+            const int row = c >> 3, ch = c & 7;
+            cp_async16(s + (((ch >> 1) * 128 + row) << 2) + ((ch & 1) << 1), g + (int64_t)(r0 + row) * ld + k0 + 2 * ch);
+        } else {
+            const int krow = c >> 6, ch = c & 63;
+            cp_async16(s + krow * 132 + 2 * ch, g + (int64_t)(k0 + krow) * ld + r0 + 2 * ch);
+        }
+    }
+}
+
+template <int LA, int LB>
+__global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmParams p) {
+    extern __shared__ __align__(128) unsigned char ws_smem[];
+    double* sA = reinterpret_cast<double*>(ws_smem);
+    double* sB = sA + WS_STAGES * TILE_DOUBLES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ws_smem + WS_STAGES * 2 * TILE_DOUBLES * sizeof(double));
+    uint64_t* empty = full + WS_STAGES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // tiles are dispatched heaviest first (longest k-range): n-major ascending when k starts at the
+    // tile's column (KLO_N), m-major descending when k stops at the tile's row (KHI_M)
+    const int tl = blockIdx.x + gridDim.x * blockIdx.y;
+    int mt = blockIdx.y, nt_ = blockIdx.x;
+    if (p.flags & KLO_N) { nt_ = tl / gridDim.y; mt = tl % gridDim.y; }
+    else if (p.flags & KHI_M) { mt = gridDim.y - 1 - tl / gridDim.x; nt_ = tl % gridDim.x; }
+    const int m0 = mt * BM, n0 = nt_ * BN;
+    if ((p.flags & LOWER_ONLY) && n0 > m0 + p.lower_shift) return;
+    const double* A = p.A + (int64_t)blockIdx.z * p.strideA;
+    const double* B = p.B + (int64_t)blockIdx.z * p.strideB;
+    int klo = 0, khi = p.K;
+    if (p.flags & KLO_M) klo = m0;
+    if ((p.flags & KLO_N) && n0 > klo) klo = n0;
+    if ((p.flags & KHI_M) && m0 + BM < khi) khi = m0 + BM;
+    const int nk = (khi > klo) ? (khi - klo) / BK : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full[s], 64); mbar_init(&empty[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= 8) {
+        // ------------------------------ cp.async producers (warp 8: A, warp 9: B) ------------------------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kt = 0; kt < nk; ++kt) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (warp == 8) ws_load_tile<LA>(sA + stage * TILE_DOUBLES, A, p.lda, m0, klo + kt * BK, lane);
+            else ws_load_tile<LB>(sB + stage * TILE_DOUBLES, B, p.ldb, n0, klo + kt * BK, lane);
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&full[stage])) : "memory");
+            if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");      // do not retire with copies (and their arrives) in flight
+        return;
+    }
+
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
+    int stage = 0;
+    uint32_t phase = 0;
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int kt = 0; kt < nk; ++kt) {
+        mbar_wait(&full[stage], phase);
+        const double* a_s = sA + stage * TILE_DOUBLES;
+        const double* b_s = sB + stage * TILE_DOUBLES;
+        double a[2][4], bb[2][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[0][i] = frag<LA>(a_s, 0, wm + i * 8, lane);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bb[0][j] = frag<LB>(b_s, 0, wn + j * 8, lane);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int cur = kk & 1, nxt = cur ^ 1;
+            if (kk < 3) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[nxt][i] = frag<LA>(a_s, kk + 1, wm + i * 8, lane);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bb[nxt][j] = frag<LB>(b_s, kk + 1, wn + j * 8, lane);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[cur][i], bb[cur][j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+    }
+    double* C = p.C + (int64_t)blockIdx.z * p.strideC;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = m0 + wm + i * 8 + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = n0 + wn + j * 8 + 2 * (lane & 3);
+            double2* dst = reinterpret_cast<double2*>(C + (int64_t)row * p.ldc + col);
+            double2 v;
+            v.x = p.alpha * acc[i][j][0];
+            v.y = p.alpha * acc[i][j][1];
+            if (p.beta != 0.0) {
+                double2 o = *dst;
+                v.x += p.beta * o.x;
+                v.y += p.beta * o.y;
+            }
+            *dst = v;
+        }
+    }
+}
+
+template <int LA, int LB>
+inline cudaError_t launch_gemm_ws(const GemmParams& p, int batch, cudaStream_t st) {
+    if (p.M <= 0 || p.N <= 0 || batch <= 0) return cudaSuccess;
+    dim3 grid(p.N / BN, p.M / BM, batch);
+    gemm_ws_kernel<LA, LB><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace abo
