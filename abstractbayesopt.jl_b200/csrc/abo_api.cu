@@ -54,7 +54,6 @@ static int configure_kernels() {
     CU(cudaFuncSetAttribute(sweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
     CU(cudaFuncSetAttribute(gemm_ws_kernel<KC, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
     CU(cudaFuncSetAttribute(gemm_ws_kernel<MC, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
-    CU(cudaFuncSetAttribute(gemm_ws_kernel<KC, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
     CU(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
     return ABO_OK;
 }
@@ -443,13 +442,17 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
 //     X21 = - X22 * (L21 * X11)
 // as two batched DMMA GEMMs that skip the structurally-zero k-ranges.  W: scratch, same shape.
 // ------------------------------------------------------------------------------------------
+static int ws_min_n() {
+    static const int v = getenv("ABO_WS_MIN") ? atoi(getenv("ABO_WS_MIN")) : 4096;
+    return v;
+}
 int trtri_blocked(abo_ctx* c, const double* L, double* Linv, double* W, int64_t Npad, int64_t ld, int64_t strideM,
                   const double* Dinv, int64_t strideD, int batch) {
     const int T = (int)(Npad / NB);
     cudaStream_t st = c->stream;
     // the warp-specialised kernel pays off once the k-loops are long; small / batched problems keep the
     // lighter barrier-synchronised kernel
-    const bool use_ws = getenv("ABO_GEMM_V1") == nullptr && Npad >= 4096;
+    const bool use_ws = Npad >= ws_min_n();
     place_diag_kernel<<<dim3(T, batch), 256, 0, st>>>(Dinv, Linv, ld, strideD, strideM);
     KL(c);
     for (int b = 1; b < T; b <<= 1) {
@@ -485,7 +488,7 @@ int trtri_blocked(abo_ctx* c, const double* L, double* Linv, double* W, int64_t 
                         g.M = rr * NB; g.N = b * NB; g.K = rr * NB; g.alpha = -1.0; g.flags = KHI_M;
                     }
                     g.lda = g.ldb = g.ldc = ld; g.strideA = g.strideB = g.strideC = zs; g.beta = 0.0;
-                    if (use_ws) CU((launch_gemm_ws<KC, MC>(g, zb, st))); else CU((launch_gemm<KC, MC, EPI_STORE>(g, zb, st)));
+                    if (use_ws) CU((launch_gemm_ws<KC, MC>(g, zb, st, c->sms))); else CU((launch_gemm<KC, MC, EPI_STORE>(g, zb, st)));
                     KL(c);
                 }
             }

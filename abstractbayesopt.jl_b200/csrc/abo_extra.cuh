@@ -210,7 +210,7 @@ extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, i
             q.A = Linv; q.B = Linv; q.C = W;
             q.lda = q.ldb = q.ldc = Npad; q.strideA = q.strideB = q.strideC = Npad * Npad;
             q.M = q.N = q.K = (int)Npad; q.alpha = 1.0; q.beta = 0.0; q.flags = KLO_M | LOWER_ONLY;
-            if (Npad >= 4096) CU((launch_gemm_ws<MC, MC>(q, nb, st)));
+            if (Npad >= ws_min_n()) CU((launch_gemm_ws<MC, MC>(q, nb, st, c->sms)));
             else CU((launch_gemm<MC, MC, EPI_STORE>(q, nb, st)));
             KL(c);
             nlml_grad_tile_kernel<<<dim3(T, T, nb), 256, 0, st>>>(spec, bt, Xb, ldx, N, W, Npad, Npad * Npad, alpha, Npad, tpart);
@@ -229,7 +229,7 @@ extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, i
             if (info) info[r0 + b] = hinfo[b];
         }
     }
-    if (3 * mat * Rc > ((size_t)2 << 30)) {        // do not sit on multi-GB scratch between calls
+    if (3 * mat * Rc > ((size_t)16 << 30)) {       // an optimiser calls this in a loop: keep up to 16 GB of scratch resident
         ws_release(c, WS_NLML_K); ws_release(c, WS_NLML_LINV); ws_release(c, WS_NLML_W);
     }
     return ABO_OK;

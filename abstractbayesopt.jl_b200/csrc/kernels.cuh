@@ -101,16 +101,17 @@ __global__ void __launch_bounds__(256) kmat_kernel(KSpec spec, const double* __r
     double* Kb = Kmat + (int64_t)blockIdx.z * bt.strideK;
     const int c = threadIdx.x & 127;
     const int64_t gc = (int64_t)bj * NB + c;
-    const int64_t j = gc / spec.p;
-    const int b = (int)(gc % spec.p);
+    const bool p1 = spec.p == 1;                       // scalar GP: no 64-bit divisions in the entry loop
+    const int64_t j = p1 ? gc : gc / spec.p;
+    const int b = p1 ? 0 : (int)(gc % spec.p);
     for (int r = threadIdx.x >> 7; r < NB; r += 2) {
         const int64_t gr = (int64_t)bi * NB + r;
         double v;
         if (gr >= N || gc >= N) {
             v = (gr == gc) ? 1.0 : 0.0;
         } else {
-            const int64_t i = gr / spec.p;
-            const int a = (int)(gr % spec.p);
+            const int64_t i = p1 ? gr : gr / spec.p;
+            const int a = p1 ? 0 : (int)(gr % spec.p);
             double u = 0.0, Da = 0.0, Db = 0.0;
             for (int k = 0; k < spec.d; ++k) {
                 double df = X[k * ldx + i] - X[k * ldx + j];
@@ -775,15 +776,18 @@ __device__ __forceinline__ double gk_dlogl_entry(const KSpec& ks, double u, doub
     const double s2 = ks.s * ks.s;
     return ks.scale * (16.0 * s2 * ddp * Da * Db + 8.0 * s2 * uphi3 * Da * Db + (a == b ? 4.0 * s2 * (dp + u * ddp) : 0.0));
 }
-__device__ __forceinline__ double u_phi3(int kind, double u) {
-    if (kind == K_SE) return -u * exp(-u / 2) / 8;
+// u times the third derivative of phi, from the second derivative ddp (no second exponential):
+//   SE: phi3 = -ddp/2;  Matern-5/2: ddp = (25/12) e^{-sqrt5 r}, phi3 = -(25 sqrt5/24) e^{-sqrt5 r} / r;
+//   Matern-7/2: ddp = (49/60)(1 + sqrt7 r) e^{-sqrt7 r}, phi3 = -(343/120) e^{-sqrt7 r}
+__device__ __forceinline__ double u_phi3(int kind, double u, double ddp) {
+    if (kind == K_SE) return -u * ddp / 2;
     const double r = sqrt(u);
     if (kind == K_M52 || kind == K_AM52 || kind == K_ADM52) {
         if (kind == K_AM52 && u < 1e-10) return 0.0;
-        return -(25.0 * 2.23606797749978969641 / 24.0) * r * exp(-2.23606797749978969641 * r);
+        return -(2.23606797749978969641 / 2.0) * r * ddp;
     }
     if (kind == K_AM72 && u < 1e-10) return 0.0;
-    return -(343.0 / 120.0) * u * exp(-2.64575131106459059050 * r);
+    return -(343.0 / 120.0) * (60.0 / 49.0) * u * ddp / (1 + 2.64575131106459059050 * r);
 }
 // per lower tile:  part[b][tile][0] = sum_ij M_ij dK_ij/dlog l ,  part[..][1] = sum_ij M_ij K_ij
 // with M = Cinv - alpha alpha^T, counted over the FULL symmetric matrix (strict-lower entries x2).
@@ -803,13 +807,14 @@ __global__ void __launch_bounds__(256) nlml_grad_tile_kernel(KSpec spec, KmatBat
         const double* al = alpha + (int64_t)blockIdx.z * strideV;
         const int c = threadIdx.x & 127;
         const int64_t gc = (int64_t)bj * NB + c;
-        const int64_t j = gc / spec.p;
-        const int b = (int)(gc % spec.p);
+        const bool p1 = spec.p == 1;
+        const int64_t j = p1 ? gc : gc / spec.p;
+        const int b = p1 ? 0 : (int)(gc % spec.p);
         for (int r = threadIdx.x >> 7; r < NB; r += 2) {
             const int64_t gr = (int64_t)bi * NB + r;
             if (gr >= N || gc >= N || gc > gr) continue;
-            const int64_t i = gr / spec.p;
-            const int a = (int)(gr % spec.p);
+            const int64_t i = p1 ? gr : gr / spec.p;
+            const int a = p1 ? 0 : (int)(gr % spec.p);
             double u = 0.0, Da = 0.0, Db = 0.0;
             for (int k = 0; k < spec.d; ++k) {
                 double df = X[k * ldx + i] - X[k * ldx + j];
@@ -820,7 +825,7 @@ __global__ void __launch_bounds__(256) nlml_grad_tile_kernel(KSpec spec, KmatBat
             double p, dp, ddp;
             phi_eval(spec.kind, u, p, dp, ddp);
             const double kv = gk_entry(spec, p, dp, ddp, a, b, Da, Db);
-            const double dk = gk_dlogl_entry(spec, u, dp, ddp, u_phi3(spec.kind, u), a, b, Da, Db);
+            const double dk = gk_dlogl_entry(spec, u, dp, ddp, p1 ? 0.0 : u_phi3(spec.kind, u, ddp), a, b, Da, Db);
             const double m = (Cb[gr * ld + gc] - al[gr] * al[gc]) * (gr == gc ? 1.0 : 2.0);
             g0 = fma(m, dk, g0);
             g1 = fma(m, kv, g1);
