@@ -95,45 +95,48 @@ def lockstep_lbfgsb(fg, x0, lower, upper, g_tol=1e-6, f_abstol=2.2e-9, max_iter=
     Returns (X, f, converged, failed)."""
     X = np.clip(np.array(x0, dtype=np.float64), lower, upper)
     R, p = X.shape
+    H = history
     f = np.full(R, np.inf); G = np.zeros((R, p))
     f[:], G[:] = fg(X, np.arange(R))
     failed = ~np.isfinite(f)                              # restart whose start already fails (bayesian_opt.jl:296-299)
     converged = np.zeros(R, dtype=bool)
-    S = [[] for _ in range(R)]; Y = [[] for _ in range(R)]
-
-    def proj_grad(x, g):
-        pg = g.copy()
-        pg[(x <= lower) & (g > 0)] = 0.0
-        pg[(x >= upper) & (g < 0)] = 0.0
-        return pg
+    # curvature pairs of all problems, oldest first in slots 0 .. cnt-1; every step below is one
+    # vectorised NumPy operation over the problems (no per-problem Python loop)
+    S = np.zeros((R, H, p)); Y = np.zeros((R, H, p)); SY = np.ones((R, H)); cnt = np.zeros(R, dtype=np.int64)
+    rows = np.arange(R)
 
     for it in range(max_iter):
-        live = np.flatnonzero(~converged & ~failed)
+        active = ~converged & ~failed
+        if not active.any():
+            break
+        PG = G.copy()
+        PG[((X <= lower) & (G > 0)) | ((X >= upper) & (G < 0))] = 0.0
+        converged |= active & (np.max(np.abs(PG), axis=1) <= g_tol)
+        active &= ~converged
+        live = np.flatnonzero(active)
         if live.size == 0:
             break
-        D = np.zeros((R, p))
-        for r in live:
-            pg = proj_grad(X[r], G[r])
-            if np.max(np.abs(pg)) <= g_tol:
-                converged[r] = True
-                continue
-            q = pg.copy(); al = []
-            for s_, y_ in zip(reversed(S[r]), reversed(Y[r])):
-                a_ = (s_ @ q) / (y_ @ s_); al.append(a_); q -= a_ * y_
-            if S[r]:
-                q *= (S[r][-1] @ Y[r][-1]) / (Y[r][-1] @ Y[r][-1])
-            else:
-                q /= max(1.0, np.linalg.norm(pg))
-            for (s_, y_), a_ in zip(zip(S[r], Y[r]), reversed(al)):
-                b_ = (y_ @ q) / (y_ @ s_); q += (a_ - b_) * s_
-            d = -q
-            d[(pg == 0.0)] = 0.0
-            if d @ G[r] >= 0:
-                d = -pg
-            D[r] = d
-        live = np.flatnonzero(~converged & ~failed)
-        if live.size == 0:
-            break
+        Q = PG.copy()
+        AL = np.zeros((R, H))
+        for h in range(H - 1, -1, -1):                     # newest to oldest
+            v = h < cnt
+            a_ = np.where(v, np.einsum("ij,ij->i", S[:, h], Q) / SY[:, h], 0.0)
+            AL[:, h] = a_
+            Q -= a_[:, None] * Y[:, h]
+        last = np.maximum(cnt - 1, 0)
+        yl = Y[rows, last]
+        gamma = np.where(cnt > 0, SY[rows, last] / np.maximum(np.einsum("ij,ij->i", yl, yl), 1e-300),
+                         1.0 / np.maximum(1.0, np.linalg.norm(PG, axis=1)))
+        Q *= gamma[:, None]
+        for h in range(H):                                 # oldest to newest
+            v = h < cnt
+            b_ = np.where(v, np.einsum("ij,ij->i", Y[:, h], Q) / SY[:, h], 0.0)
+            Q += np.where(v, AL[:, h] - b_, 0.0)[:, None] * S[:, h]
+        D = -Q
+        D[PG == 0.0] = 0.0
+        up = np.einsum("ij,ij->i", D, G) >= 0              # not a descent direction: steepest descent
+        D[up] = -PG[up]
+        D[~active] = 0.0
         t = np.ones(R)
         pending = live.copy()
         Xn = X.copy(); fn = f.copy(); Gn = G.copy()
@@ -150,15 +153,18 @@ def lockstep_lbfgsb(fg, x0, lower, upper, g_tol=1e-6, f_abstol=2.2e-9, max_iter=
                 break
             t[pending] *= 0.5
         converged[pending] = True                          # no further progress along a descent direction
-        moved = np.setdiff1d(live, pending)
-        for r in moved:
-            s_ = Xn[r] - X[r]; y_ = Gn[r] - G[r]
-            if s_ @ y_ > 1e-12 * np.linalg.norm(s_) * np.linalg.norm(y_):
-                S[r].append(s_); Y[r].append(y_)
-                if len(S[r]) > history:
-                    S[r].pop(0); Y[r].pop(0)
-            if abs(f[r] - fn[r]) <= f_abstol:
-                converged[r] = True
+        moved = active.copy(); moved[pending] = False
+        Sn = Xn - X; Yn = Gn - G
+        sy = np.einsum("ij,ij->i", Sn, Yn)
+        keep = moved & (sy > 1e-12 * np.linalg.norm(Sn, axis=1) * np.linalg.norm(Yn, axis=1))
+        full = keep & (cnt == H)                           # drop the oldest pair where the history is full
+        if full.any():
+            S[full, :-1] = S[full, 1:]; Y[full, :-1] = Y[full, 1:]; SY[full, :-1] = SY[full, 1:]
+            cnt[full] -= 1
+        kr = np.flatnonzero(keep)
+        S[kr, cnt[kr]] = Sn[kr]; Y[kr, cnt[kr]] = Yn[kr]; SY[kr, cnt[kr]] = sy[kr]
+        cnt[kr] += 1
+        converged |= moved & (np.abs(f - fn) <= f_abstol)
         X, f, G = Xn, fn, Gn
     return X, f, converged, failed
 
