@@ -99,6 +99,7 @@ extern "C" int32_t abo_ctx_destroy(abo_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& b : c->ws) if (b.ptr) cudaFree(b.ptr);
+    gp_pool_clear(c);
     for (auto e : c->prof_events) cudaEventDestroy(e);
     if (c->pinned) cudaFreeHost(c->pinned);
     abo_nccl_teardown(c);
@@ -525,32 +526,114 @@ int solve_alpha(abo_ctx* c, const double* Linv, int64_t ld, int64_t N, const dou
 // ------------------------------------------------------------------------------------------
 // surrogate handle
 // ------------------------------------------------------------------------------------------
+// Device buffers are reference counted: abo_gp_clone shares them (O(1), Base.copy of a posterior in
+// the BO loop, bayesian_opt.jl:116) and a handle that is about to WRITE takes a private set first
+// (gp_alloc for a re-fit, gp_unshare for an append).  Released sets go to a small per-context pool.
+constexpr size_t GP_POOL_MAX_SETS = 3;
+constexpr size_t GP_POOL_MAX_BYTES = (size_t)24 << 30;
+static size_t gp_set_bytes(int64_t cap_pad) { return 2 * sizeof(double) * (size_t)cap_pad * cap_pad; }
+
 static void gp_free_device(abo_gp* g) {
     cudaSetDevice(g->ctx->device);
     double** ptrs[] = {&g->dXsT, &g->dL, &g->dLinv, &g->dAlpha, &g->dBeta, &g->dDelta, &g->dMeanC};
-    for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+    if (g->share && --*g->share == 0) {
+        delete g->share;
+        abo_ctx* c = g->ctx;
+        size_t pooled = 0;
+        for (auto& e : c->gp_pool) pooled += gp_set_bytes(e.cap_pad);
+        if (g->dL && c->gp_pool.size() < GP_POOL_MAX_SETS && pooled + gp_set_bytes(g->cap_pad) <= GP_POOL_MAX_BYTES) {
+            abo_ctx::GpBufSet e{g->cap_pad, g->ldx, g->d, g->p, {}};
+            for (int q = 0; q < 7; ++q) e.ptr[q] = *ptrs[q];
+            c->gp_pool.push_back(e);
+        } else {
+            for (auto pp : ptrs) if (*pp) cudaFree(*pp);
+        }
+    }
+    for (auto pp : ptrs) *pp = nullptr;
+    g->share = nullptr;
     g->fitted = false;
     g->cap_pad = 0;
 }
 
+void gp_pool_clear(abo_ctx* c) {
+    for (auto& e : c->gp_pool) for (double* q : e.ptr) if (q) cudaFree(q);
+    c->gp_pool.clear();
+}
+
 int gp_alloc(abo_gp* g, int64_t Npad, int64_t ldx) {
     gp_free_device(g);
+    abo_ctx* c = g->ctx;
+    double** ptrs[] = {&g->dXsT, &g->dL, &g->dLinv, &g->dAlpha, &g->dBeta, &g->dDelta, &g->dMeanC};
+    g->share = new (std::nothrow) int(1);
+    if (!g->share) return abo_fail(ABO_ERR_ALLOC, "host allocation failed");
+    for (size_t q = 0; q < c->gp_pool.size(); ++q) {
+        auto& e = c->gp_pool[q];
+        if (e.cap_pad == Npad && e.ldx == ldx && e.d == g->d && e.p == g->p) {
+            for (int r = 0; r < 7; ++r) *ptrs[r] = e.ptr[r];
+            c->gp_pool.erase(c->gp_pool.begin() + q);
+            g->cap_pad = Npad; g->ld = Npad; g->ldx = ldx;
+            return ABO_OK;
+        }
+    }
     size_t mat = sizeof(double) * (size_t)Npad * Npad;
-    cudaError_t e;
-    if ((e = cudaMalloc(&g->dL, mat)) != cudaSuccess || (e = cudaMalloc(&g->dLinv, mat)) != cudaSuccess ||
-        (e = cudaMalloc(&g->dXsT, sizeof(double) * (size_t)ldx * g->d)) != cudaSuccess ||
-        (e = cudaMalloc(&g->dAlpha, sizeof(double) * Npad)) != cudaSuccess ||
-        (e = cudaMalloc(&g->dBeta, sizeof(double) * Npad)) != cudaSuccess ||
-        (e = cudaMalloc(&g->dDelta, sizeof(double) * Npad)) != cudaSuccess ||
-        (e = cudaMalloc(&g->dMeanC, sizeof(double) * g->p)) != cudaSuccess) {
+    cudaError_t e = cudaSuccess;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if ((e = cudaMalloc(&g->dL, mat)) == cudaSuccess && (e = cudaMalloc(&g->dLinv, mat)) == cudaSuccess &&
+            (e = cudaMalloc(&g->dXsT, sizeof(double) * (size_t)ldx * g->d)) == cudaSuccess &&
+            (e = cudaMalloc(&g->dAlpha, sizeof(double) * Npad)) == cudaSuccess &&
+            (e = cudaMalloc(&g->dBeta, sizeof(double) * Npad)) == cudaSuccess &&
+            (e = cudaMalloc(&g->dDelta, sizeof(double) * Npad)) == cudaSuccess &&
+            (e = cudaMalloc(&g->dMeanC, sizeof(double) * g->p)) == cudaSuccess)
+            break;
         cudaGetLastError();
-        gp_free_device(g);
+        for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+        if (attempt == 0 && !c->gp_pool.empty()) { gp_pool_clear(c); continue; }   // give the pooled sets back and retry
+        delete g->share; g->share = nullptr;
         return abo_fail(ABO_ERR_ALLOC, "device allocation for a %lld x %lld posterior failed: %s", (long long)Npad,
                         (long long)Npad, cudaGetErrorString(e));
     }
     g->cap_pad = Npad;
     g->ld = Npad;
     g->ldx = ldx;
+    return ABO_OK;
+}
+
+// private copy of shared buffers before an in-place update (copy-on-write): the lower tiles of L and
+// L^-1 (the upper ones are never read), the coordinates and the vectors
+__global__ void copy_lower_tiles_kernel(const double* __restrict__ a0, const double* __restrict__ a1, double* __restrict__ b0,
+                                        double* __restrict__ b1, int64_t ld) {
+    if (blockIdx.x > blockIdx.y) return;
+    const double* src = blockIdx.z ? a1 : a0;
+    double* dst = blockIdx.z ? b1 : b0;
+    const int64_t base = (int64_t)blockIdx.y * NB * ld + (int64_t)blockIdx.x * NB;
+    for (int e = threadIdx.x; e < NB * NB / 2; e += blockDim.x) {
+        const int r = e / (NB / 2), c2 = e % (NB / 2);
+        reinterpret_cast<double2*>(dst + base + (int64_t)r * ld)[c2] = reinterpret_cast<const double2*>(src + base + (int64_t)r * ld)[c2];
+    }
+}
+
+int gp_unshare(abo_gp* g) {
+    if (!gp_shared(g)) return ABO_OK;
+    abo_ctx* c = g->ctx;
+    cudaStream_t st = c->stream;
+    abo_gp old = *g;                                    // keeps the shared pointers; its count is dropped below
+    g->dXsT = g->dL = g->dLinv = g->dAlpha = g->dBeta = g->dDelta = g->dMeanC = nullptr;
+    g->share = nullptr;
+    const bool fitted = old.fitted;
+    int rc = gp_alloc(g, old.cap_pad, old.ldx);         // gp_free_device on the nulled handle is a no-op
+    if (rc) { *g = old; return rc; }
+    const int T = (int)(old.cap_pad / NB);
+    copy_lower_tiles_kernel<<<dim3(T, T, 2), 256, 0, st>>>(old.dL, old.dLinv, g->dL, g->dLinv, old.ld);
+    KL(c);
+    CU(cudaMemcpyAsync(g->dXsT, old.dXsT, sizeof(double) * old.ldx * old.d, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(g->dAlpha, old.dAlpha, sizeof(double) * old.cap_pad, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(g->dBeta, old.dBeta, sizeof(double) * old.cap_pad, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(g->dDelta, old.dDelta, sizeof(double) * old.cap_pad, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(g->dMeanC, old.dMeanC, sizeof(double) * old.p, cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    --*old.share;                                       // > 0 by construction: the other holders keep the set
+    old.hX.clear(); old.hY.clear();
+    g->fitted = fitted;
     return ABO_OK;
 }
 
@@ -605,7 +688,7 @@ extern "C" int32_t abo_gp_fit(abo_gp* g, const double* X, const double* y, int64
     const int64_t Npad = (N + NB - 1) / NB * NB;
     const int64_t ldx = (n + NB - 1) / NB * NB + NB;      // room for appended points
     g->fitted = false;
-    if (Npad != g->cap_pad || ldx > g->ldx) { int rc = gp_alloc(g, Npad, ldx); if (rc) return rc; }
+    if (Npad != g->cap_pad || ldx > g->ldx || gp_shared(g)) { int rc = gp_alloc(g, Npad, ldx); if (rc) return rc; }
     g->n = n; g->N = N; g->Npad = Npad;
     g->hX.assign(X, X + n * g->d);
     g->hY.assign(y, y + N);
@@ -653,27 +736,9 @@ extern "C" int32_t abo_gp_fit(abo_gp* g, const double* X, const double* y, int64
 
 extern "C" int32_t abo_gp_clone(const abo_gp* g, abo_gp** out) {
     if (!g || !out) return abo_fail(ABO_ERR_INVALID, "null argument");
-    abo_gp* n = new (std::nothrow) abo_gp(*g);
+    abo_gp* n = new (std::nothrow) abo_gp(*g);          // shares the device buffers; a writer un-shares first
     if (!n) return abo_fail(ABO_ERR_ALLOC, "host allocation failed");
-    n->dXsT = n->dL = n->dLinv = n->dAlpha = n->dBeta = n->dDelta = n->dMeanC = nullptr;
-    n->cap_pad = 0; n->fitted = false;
-    if (g->cap_pad > 0) {
-        abo_ctx* c = g->ctx;
-        CU(cudaSetDevice(c->device));
-        int rc = gp_alloc(n, g->cap_pad, g->ldx);
-        if (rc) { delete n; return rc; }
-        cudaStream_t st = c->stream;
-        size_t mat = sizeof(double) * (size_t)g->cap_pad * g->cap_pad;
-        CU(cudaMemcpyAsync(n->dL, g->dL, mat, cudaMemcpyDeviceToDevice, st));
-        CU(cudaMemcpyAsync(n->dLinv, g->dLinv, mat, cudaMemcpyDeviceToDevice, st));
-        CU(cudaMemcpyAsync(n->dXsT, g->dXsT, sizeof(double) * g->ldx * g->d, cudaMemcpyDeviceToDevice, st));
-        CU(cudaMemcpyAsync(n->dAlpha, g->dAlpha, sizeof(double) * g->cap_pad, cudaMemcpyDeviceToDevice, st));
-        CU(cudaMemcpyAsync(n->dBeta, g->dBeta, sizeof(double) * g->cap_pad, cudaMemcpyDeviceToDevice, st));
-        CU(cudaMemcpyAsync(n->dDelta, g->dDelta, sizeof(double) * g->cap_pad, cudaMemcpyDeviceToDevice, st));
-        CU(cudaMemcpyAsync(n->dMeanC, g->dMeanC, sizeof(double) * g->p, cudaMemcpyDeviceToDevice, st));
-        CU(cudaStreamSynchronize(st));
-        n->fitted = g->fitted;
-    }
+    if (n->share) ++*n->share;
     *out = n;
     return ABO_OK;
 }
@@ -707,6 +772,8 @@ extern "C" int32_t abo_gp_factor(const abo_gp* g, int32_t which, double* out) {
     CU(cudaMemcpy2DAsync(out, sizeof(double) * g->N, src, sizeof(double) * g->ld, sizeof(double) * g->N, g->N,
                          cudaMemcpyDeviceToHost, g->ctx->stream));
     CU(cudaStreamSynchronize(g->ctx->stream));
+    for (int64_t i = 0; i < g->N; ++i)                  // tiles above the diagonal are never written on the device
+        for (int64_t j = i + 1; j < g->N; ++j) out[i * g->N + j] = 0.0;
     return ABO_OK;
 }
 

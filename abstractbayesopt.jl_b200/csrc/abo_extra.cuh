@@ -123,6 +123,7 @@ extern "C" int32_t abo_gp_append(abo_gp* g, const double* x, const double* y, in
         reduce_rows_kernel<<<dim3((unsigned)((n + 127) / 128), 1), 128, 0, st>>>(part, nchunks, n, r, 0, 0);
         KL(c);
     }
+    if ((rc = gp_unshare(g))) return rc;      // copy-on-write: clones keep the un-appended posterior
     if (n + 1 > g->cap_pad) {                 // no padding row left: one more tile
         if ((rc = grow_capacity(g))) return rc;
     }

@@ -55,6 +55,9 @@ struct abo_ctx {
     // NCCL (one rank per context)
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    // released posterior buffer sets kept for re-use (a BO loop allocates and frees one per iteration)
+    struct GpBufSet { int64_t cap_pad, ldx; int d, p; double* ptr[7]; };
+    std::vector<GpBufSet> gp_pool;
 };
 
 struct abo_gp {
@@ -67,6 +70,7 @@ struct abo_gp {
     bool fitted = false;
     double *dXsT = nullptr, *dL = nullptr, *dLinv = nullptr, *dAlpha = nullptr, *dBeta = nullptr,
            *dDelta = nullptr, *dMeanC = nullptr;
+    int* share = nullptr;                 // reference count of the device buffers (clones share them until one writes)
     std::vector<double> hX, hY;           // host copies of the conditioning data (ABI layout)
 };
 
@@ -79,6 +83,9 @@ static inline uint64_t ordkey(double v) {
 }
 
 int gp_alloc(abo_gp* g, int64_t Npad, int64_t ldx);
+int gp_unshare(abo_gp* g);
+void gp_pool_clear(abo_ctx* c);
+static inline bool gp_shared(const abo_gp* g) { return g->share && *g->share > 1; }
 void ws_release(abo_ctx* c, int slot);
 int ws_get(abo_ctx* c, int slot, size_t bytes, void** out);
 int pinned_get(abo_ctx* c, size_t bytes, void** out);

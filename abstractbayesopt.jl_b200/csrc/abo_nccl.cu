@@ -126,7 +126,7 @@ extern "C" int32_t abo_gp_sync(abo_gp* g, int32_t root) {
         for (int a = 0; a < g->p; ++a) g->mean_c[a] = h[16 + a];
         const int64_t cap = (int64_t)h[10], ldx = (int64_t)h[3];
         g->fitted = false;
-        if (cap != g->cap_pad || ldx != g->ldx) { if ((rc = gp_alloc(g, cap, ldx))) return rc; }
+        if (cap != g->cap_pad || ldx != g->ldx || gp_shared(g)) { if ((rc = gp_alloc(g, cap, ldx))) return rc; }
         g->n = (int64_t)h[0]; g->N = (int64_t)h[1]; g->Npad = (int64_t)h[2];
         g->hX.clear(); g->hY.clear();
     }

@@ -91,7 +91,10 @@ int32_t abo_gp_fit(abo_gp* gp, const double* X, const double* y, int64_t n, int6
 /* O(n^2) row append of one observation (x[d], y[p]); transactional: on ABO_ERR_NOT_POSDEF the
  * handle still holds the previous posterior.  (The reference re-fits: bayesian_opt.jl:125.) */
 int32_t abo_gp_append(abo_gp* gp, const double* x, const double* y, int64_t* info);
-/* Base.copy(::StandardGP) (StandardGP.jl:26, surrogates_utils.jl:12-14): deep copy on device */
+/* Base.copy(::StandardGP) (StandardGP.jl:26, surrogates_utils.jl:12-14).  Value semantics of a deep
+ * copy at O(1) cost: the clone shares the device buffers (reference counted) and whichever handle
+ * is written next (abo_gp_fit, abo_gp_append, the receiving side of abo_gp_sync) first takes a
+ * private set — copy-on-write.  The BO loop's per-iteration snapshot (bayesian_opt.jl:116) is free. */
 int32_t abo_gp_clone(const abo_gp* gp, abo_gp** out);
 int32_t abo_gp_n(const abo_gp* gp, int64_t* n);
 /* read back alpha (N = n*p, out-major) — PosteriorGP.data.α */

@@ -246,6 +246,39 @@ def test_append_is_transactional(abo, orc):
     assert m1[0] == m0[0] and v1[0] == v0[0]
 
 
+def test_clone_is_copy_on_write(abo, orc):
+    """abo_gp_clone shares the device buffers; every writer (append, re-fit, destroy) must leave the
+    other holders' posterior bit-identical (value semantics of Base.copy, StandardGP.jl:26)."""
+    c = orc.make_config("C4", n=250, m=400, d=5)
+    k = make_kernel(abo, c["kind"], c["inv_ls"], c["scale"])
+    gp = abo.update(abo.StandardGP(k, c["noise"]), c["X"], c["y"])
+    h0 = gp.gpx
+    m0, v0 = h0.posterior(c["Xc"])
+    L0 = h0.factor(0)
+    h1 = h0.clone(); h2 = h0.clone()
+    h1.append(c["Xc"][0], [0.1])                                  # writer 1: append on a clone (crosses 256 -> grows later)
+    for i in range(1, 8):
+        h1.append(c["Xc"][i], [0.1 * i])
+    assert h1.n() == 258 and h0.n() == 250 and h2.n() == 250
+    for h in (h0, h2):
+        m, v = h.posterior(c["Xc"])
+        assert np.array_equal(m, m0) and np.array_equal(v, v0) and np.array_equal(h.factor(0), L0)
+    Xa = np.vstack([c["X"], c["Xc"][:8]]); ya = np.concatenate([c["y"], 0.1 * np.arange(8)]); ya[250] = 0.1
+    ref = abo.GpHandle(abo.default_context(), c["kind"], 5, 1); ref.set_params(c["inv_ls"], c["scale"], c["noise"]); ref.fit(Xa, ya)
+    ma, va = h1.posterior(c["Xc"][20:]); mr, vr = ref.posterior(c["Xc"][20:])
+    assert close(ma, mr, 1.0, 1e-10) and close(va, vr, 1.0, 1e-10)
+    h2.set_params(2 * c["inv_ls"], c["scale"], c["noise"]); h2.fit(c["X"][:100], c["y"][:100])     # writer 2: re-fit of a sharer
+    assert h2.n() == 100
+    m, v = h0.posterior(c["Xc"])
+    assert np.array_equal(m, m0) and np.array_equal(v, v0)
+    h3 = h0.clone()
+    h0.close()                                                     # writer 3: the original goes away
+    m, v = h3.posterior(c["Xc"])
+    assert np.array_equal(m, m0) and np.array_equal(v, v0)
+    h3.append(c["Xc"][0], [0.1])                                  # sole owner now: in place, still correct
+    assert h3.n() == 251
+
+
 # ---- batched NLML + analytic gradient (StandardGP.jl:99-114, bayesian_opt.jl:259-300) ------
 def test_nlml_known_answer(abo):
     gp = abo.StandardGP(abo.SqExponentialKernel(), 0.1)

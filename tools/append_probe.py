@@ -14,8 +14,16 @@ for i in range(n, n + 40):
     t0 = time.perf_counter(); h.append(c["X"][i], c["y"][i:i + 1]); ts.append(time.perf_counter() - t0)
 t = float(np.median(ts[5:]))
 t0 = time.perf_counter(); h2 = gp.gpx.clone(); t_clone = time.perf_counter() - t0
+# the BO loop's step (bayesian_opt.jl:113-150): snapshot copy + functional update with one more observation;
+# the update un-shares the snapshot's buffers (copy-on-write) and appends
+tb = []
+g = gp
+for i in range(n, n + 12):
+    t0 = time.perf_counter(); prev = g.copy(); g = abo.update(g, c["X"][:i + 1], c["y"][:i + 1]); tb.append(time.perf_counter() - t0)
+t_bo = float(np.median(tb[3:]))
 bytes_alg = 2 * (n * (n + 1) / 2) * 8
 peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
     if os.path.exists("MEASURED_PEAKS.json") else 6548.2
 print(json.dumps({"n": n, "append_ms_median": 1e3 * t, "algorithmic_GB": bytes_alg / 1e9, "achieved_GBs": bytes_alg / t / 1e9,
-                  "hbm_peak_GBs": peak, "frac": bytes_alg / t / 1e9 / peak, "clone_ms": 1e3 * t_clone}))
+                  "hbm_peak_GBs": peak, "frac": bytes_alg / t / 1e9 / peak, "clone_ms": 1e3 * t_clone,
+                  "bo_update_ms_copy_plus_append": 1e3 * t_bo}))
