@@ -355,6 +355,34 @@ def test_bo_loop_branin(abo, orc):
     assert all(a >= 0 for a in acq_list)
 
 
+def test_bo_loop_gradient_gp(abo, orc):
+    # GradientGP + EI on Himmelblau with analytic gradients (the 2-D tutorial's objective, docs 2D_BO.jl:19-22),
+    # hyper-parameters re-optimised in the loop, standardisation "scale_only" as the gradient tutorials use
+    rng = np.random.default_rng(3)
+    dom = abo.ContinuousDomain([-6.0, -6.0], [6.0, 6.0])
+
+    def f(x):
+        x1, x2 = float(x[0]), float(x[1])
+        a, b = x1 * x1 + x2 - 11.0, x1 + x2 * x2 - 7.0
+        return np.array([a * a + b * b, 4 * x1 * a + 2 * b, 2 * a + 4 * x2 * b])
+
+    X0 = dom.lower + (dom.upper - dom.lower) * rng.random((6, 2))
+    y0 = [f(x) for x in X0]
+    gp = abo.GradientGP(1.0 * abo.with_lengthscale(abo.ApproxMatern52Kernel(), 2.0), 3, 1e-8)
+    best0 = min(float(v[0]) for v in y0)
+    bo = abo.BOStruct(f, abo.ExpectedImprovement(0.0, best0), gp, dom, list(X0), y0, 11, 0.0)
+    bo, acq_list, (mu, sd) = abo.optimize(bo, standardize="scale_only", hyper_params="all", num_restarts_HP=2,
+                                         n_grid=3000, n_local=8, rng=rng)
+    assert bo.flag or len(bo.xs) == 6 + 12
+    assert len(bo.ys_non_std) == len(bo.xs) and all(np.asarray(v).shape == (3,) for v in bo.ys_non_std)
+    assert min(float(v[0]) for v in bo.ys_non_std) <= best0
+    assert isinstance(bo.model, abo.GradientGP) and bo.model.gpx.n() == len(bo.xs)
+    # the surrogate interpolates value AND gradient at the data (noise 1e-8) in standardised units
+    Xd = np.array(bo.xs); Yd = np.array(bo.ys)
+    gm = abo.posterior_grad_mean(bo.model, Xd).reshape(3, -1).T
+    assert np.max(np.abs(gm - Yd)) <= 1e-3 * max(1.0, np.max(np.abs(Yd)))
+
+
 # ---- BASELINE.json configurations at FULL size: a seeded sample of the sweep against the oracle
 #      plus size-independent properties (top-k consistency, determinism, shard independence) ----
 def _sample_check(abo, orc, gp, post, Xc, acq, acq_id, scale, nsample=3000, seed=0):
