@@ -15,7 +15,8 @@ from .surrogates import (AbstractSurrogate, GradientGP, StandardGP, get_kernel_c
 from .acquisition import (AbstractAcquisition, EnsembleAcquisition, ExpectedImprovement, GradientNormUCB,
                           ProbabilityImprovement, UpperConfidenceBound)
 from .domains import AbstractDomain, ContinuousDomain
-from .parallel import init_nccl_context, merge_topk, shard_range, sharded_topk, sync_posterior
+from .parallel import (init_nccl_context, merge_topk, shard_range, sharded_nlml_batch, sharded_restarts, sharded_topk,
+                       sync_posterior)
 from .bayesian_opt import (BOStruct, latin_hypercube, lengthscale_bounds, lockstep_lbfgsb, monte_carlo_fill_distance, optimize, optimize_acquisition, optimize_hyperparameters,
                            standardize_problem, stop_criteria, update_bo)
 

@@ -19,7 +19,7 @@ SYMBOLS = [
     "abo_ctx_launch_count", "abo_ctx_profile", "abo_ctx_profile_read", "abo_debug_potf2_clocks", "abo_gp_create", "abo_gp_destroy", "abo_gp_set_params", "abo_gp_fit", "abo_gp_append",
     "abo_gp_clone", "abo_gp_n", "abo_gp_alpha", "abo_gp_factor", "abo_gp_posterior", "abo_gp_posterior_cov", "abo_acq_eval", "abo_acq_eval_dev", "abo_acq_eval_grad",
     "abo_nlml_batch", "abo_potrf_dev", "abo_fill_distance", "abo_nccl_unique_id", "abo_ctx_init_rank", "abo_gp_sync",
-    "abo_topk_allgather",
+    "abo_topk_allgather", "abo_allgather_f64",
 ]
 
 
@@ -85,6 +85,7 @@ def lib():
             "abo_ctx_init_rank": [vp, i32, i32, vp],
             "abo_gp_sync": [vp, i32],
             "abo_topk_allgather": [vp, i64, i64, vp, vp, C.POINTER(i64)],
+            "abo_allgather_f64": [vp, vp, i64, vp],
         }
         for name, args in sigs.items():
             f = getattr(L, name)
@@ -175,6 +176,13 @@ class Context:
         out = C.c_int64(0)
         check(lib().abo_topk_allgather(self._h, k, cnt, ptr(ti), ptr(tv), C.byref(out)))
         return ti[:out.value], tv[:out.value]
+
+    def allgather_f64(self, send, nranks: int):
+        """NCCL all-gather of equally sized float64 blocks; returns an (nranks, len(send)) array."""
+        send = f64(np.ravel(send))
+        recv = np.empty((nranks, send.size))
+        check(lib().abo_allgather_f64(self._h, ptr(send), send.size, ptr(recv)))
+        return recv
 
     def close(self):
         if self._h is not None and self._h.value:

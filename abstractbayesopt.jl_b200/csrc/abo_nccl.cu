@@ -194,3 +194,22 @@ extern "C" int32_t abo_topk_allgather(abo_ctx* c, int64_t k, int64_t count, int6
     abo_merge_topk(items, vals, k, top_idx, top_val, out_count);
     return ABO_OK;
 }
+
+// all-gather of `count` doubles per rank (host buffers; results of the sharded NLML restarts,
+// SURVEY 8e): recv holds nranks * count values in rank order
+extern "C" int32_t abo_allgather_f64(abo_ctx* c, const double* send, int64_t count, double* recv) {
+    if (!c || !send || !recv) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (count < 0) return abo_fail(ABO_ERR_INVALID, "negative count");
+    if (count == 0) return ABO_OK;
+    if (c->nranks == 1) { memcpy(recv, send, sizeof(double) * count); return ABO_OK; }
+    if (!c->nccl_comm) return abo_fail(ABO_ERR_NCCL, "context has no NCCL communicator (abo_ctx_init_rank)");
+    CU(cudaSetDevice(c->device));
+    double* d;
+    int rc = ws_get(c, WS_TOPK, sizeof(double) * (size_t)count * (c->nranks + 1), (void**)&d);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(d, send, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
+    NC(nccl().allGather(d, d + count, (size_t)count, NCCL_FLOAT64, c->nccl_comm, c->stream));
+    CU(cudaMemcpyAsync(recv, d + count, sizeof(double) * count * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return ABO_OK;
+}

@@ -50,6 +50,43 @@ def sharded_topk(acq, surrogate, candidates, k: int, group=None):
     return merge_topk([g[0] for g in gathered], [g[1] for g in gathered], k)
 
 
+def sharded_restarts(evaluate, logparams, group=None, nccl_ctx=None):
+    """NLML restarts sharded R/G per rank: rank r evaluates rows [r*R/G, (r+1)*R/G) of
+    `logparams` with `evaluate(rows) -> (val[R_r], grad[R_r, 2], info[R_r])` (abo_nlml_batch on its GPU) and
+    every rank ends up with the full (val, grad, info) in restart order.  The exchange is one
+    all-gather of 4 doubles per restart: NCCL through the context when `nccl_ctx` has a
+    communicator, else the torch.distributed group (gloo in the CPU tests)."""
+    import torch.distributed as dist
+    theta = np.asarray(logparams, dtype=np.float64).reshape(-1, 2)
+    R = theta.shape[0]
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_range(R, rank, world)
+    val, grad, info = evaluate(theta[lo:hi])
+    if world == 1:
+        return np.asarray(val), np.asarray(grad), np.asarray(info)
+    per = -(-R // world)                                   # equal-sized blocks, padded
+    block = np.zeros((per, 4))
+    block[:hi - lo, 0] = val; block[:hi - lo, 1:3] = np.asarray(grad).reshape(-1, 2); block[:hi - lo, 3] = info
+    if nccl_ctx is not None:
+        allb = nccl_ctx.allgather_f64(block, world).reshape(world, per, 4)
+    else:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, block, group=group)
+        allb = np.stack(gathered)
+    out = np.concatenate([allb[r, :shard_range(R, r, world)[1] - shard_range(R, r, world)[0]] for r in range(world)])
+    return out[:, 0].copy(), out[:, 1:3].copy(), out[:, 3].astype(np.int32)
+
+
+def sharded_nlml_batch(model, logparams, xs, ys, group=None, use_nccl=True):
+    """nlml + gradient for all restarts with the restarts split across the ranks' GPUs."""
+    from .surrogates import nlml_batch
+    from ._lib import default_context
+    ctx = model.ctx or default_context()
+    return sharded_restarts(lambda th: nlml_batch(model, th, xs, ys), logparams, group=group,
+                            nccl_ctx=ctx if use_nccl else None)
+
+
 def init_nccl_context(ctx, group=None):
     """Give `ctx` an NCCL rank matching the torch.distributed group: rank 0 creates the NCCL
     unique id, it is broadcast through the existing process group (any backend)."""

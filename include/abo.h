@@ -161,6 +161,10 @@ int32_t abo_gp_sync(abo_gp* gp, int32_t root);
 int32_t abo_topk_allgather(abo_ctx* ctx, int64_t k, int64_t count, int64_t* top_idx, double* top_val,
                            int64_t* out_count);
 
+/* all-gather `count` doubles per rank in rank order (recv: nranks * count); used for the results of
+ * NLML restarts sharded R/G per rank (bayesian_opt.jl:264-300 runs them one after the other) */
+int32_t abo_allgather_f64(abo_ctx* ctx, const double* send, int64_t count, double* recv);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,7 +59,16 @@ def _worker(rank, world, port, q):
     rng = np.random.default_rng(3)
     cand = rng.random((10_001, 2))
     gi, gv = abo.sharded_topk(FakeAcq(), None, cand, 50)
-    q.put((rank, gi.tolist(), gv.tolist()))
+    # NLML restarts sharded R/G (R = 7 is not divisible by 2): a closed-form stand-in for abo_nlml_batch
+    theta = np.random.default_rng(5).normal(size=(7, 2))
+    calls = []
+
+    def fake_eval(th):
+        calls.append(len(th))
+        return (th ** 2).sum(1), 2 * th, (th[:, 0] > 1.0).astype(np.int32)
+
+    v, g, info = abo.sharded_restarts(fake_eval, theta)
+    q.put((rank, gi.tolist(), gv.tolist(), v.tolist(), g.tolist(), info.tolist(), calls))
     dist.destroy_process_group()
 
 
@@ -76,5 +85,9 @@ def test_sharded_topk_gloo_world2():
     cand = rng.random((10_001, 2))
     sc = np.sin(37.0 * cand[:, 0]) * np.cos(11.0 * cand[:, 1])
     ref = orc.sortperm_rev(sc, 50)
-    for rank, gi, gv in out:
+    theta = np.random.default_rng(5).normal(size=(7, 2))
+    for rank, gi, gv, v, g, info, calls in out:
         assert gi == list(ref)
+        assert np.array_equal(np.array(v), (theta ** 2).sum(1)) and np.array_equal(np.array(g), 2 * theta)
+        assert info == (theta[:, 0] > 1.0).astype(int).tolist()
+        assert calls == [3 if rank == 0 else 4]                       # each rank evaluated only its shard

@@ -34,9 +34,15 @@ _, ti, tv = acq.topk(model, c["Xc"][lo:hi], 100)
 gi, gv = ctx.topk_allgather(100, ti + lo, tv)
 gi2, gv2 = abo.sharded_topk(acq, model, c["Xc"], 100)
 assert list(gi) == list(gi2) and np.array_equal(gv, gv2)
+# NLML restarts sharded R/G per rank, results all-gathered over NCCL: identical to the single-GPU batch
+c5 = orc.make_config("C5", n=300, m=13)
+gp0 = abo.StandardGP(abo.SqExponentialKernel(), c5["noise"], ctx=ctx)
+v_s, g_s, i_s = abo.sharded_nlml_batch(gp0, c5["theta"], c5["X"], c5["y"])
+v_1, g_1, i_1 = abo.nlml_batch(gp0, c5["theta"], c5["X"], c5["y"])
+assert np.array_equal(v_s, v_1) and np.array_equal(g_s, g_1) and np.array_equal(i_s, i_1), "sharded NLML differs"
 if rank == 0:
     s_all, ti_all, tv_all = acq.topk(model, c["Xc"], 100)
     assert list(ti_all) == list(gi), "sharded top-k differs from the single-GPU top-k"
     N = 1536
-    print(f"nccl_check ok: world={world} sync of {2 * N * N * 8 / 1e6:.1f} MB in {dt * 1e3:.2f} ms; top-k identical", flush=True)
+    print(f"nccl_check ok: world={world} sync of {2 * N * N * 8 / 1e6:.1f} MB in {dt * 1e3:.2f} ms; top-k and sharded NLML identical", flush=True)
 dist.destroy_process_group()
