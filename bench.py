@@ -355,8 +355,33 @@ def main():
                 best = min(best, s0.elapsed_time(s1))
         fl = n ** 3 / 3.0 + n ** 2 / 2.0
         chol = {"n": n, "ms": best, "tflops": fl / (best * 1e-3) / 1e12, "frac_of_peak": fl / (best * 1e-3) / 1e12 / peak,
-                "fit_total_s": t_fit}
+                "first_fit_s_incl_allocation": t_fit}
         del K0, A, Xd
+        # the whole conditioning step (K build + Cholesky + triangular inverse + alpha), warm, through the host API
+        tw = []
+        for _ in range(3):
+            t1 = time.perf_counter(); abo.update(model, c["X"], c["y"], allow_append=False); tw.append(time.perf_counter() - t1)
+        chol["fit_ms_warm"] = 1e3 * min(tw)
+        # a larger factorisation: the look-ahead schedule approaches the GEMM rate as the panel share shrinks
+        n2 = 2 * n
+        X2 = torch.rand((n2, DIM), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7))
+        K2 = torch.exp(-0.5 * torch.cdist(X2, X2) ** 2) + 1e-2 * torch.eye(n2, dtype=torch.float64, device="cuda")
+        A2 = torch.empty_like(K2)
+        best2 = 1e30
+        for it in range(3):
+            A2.copy_(K2)
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(lib_stream)
+            ctx.potrf_dev(A2.data_ptr(), n2, n2)
+            s1.record(lib_stream)
+            torch.cuda.synchronize()
+            if it:
+                best2 = min(best2, s0.elapsed_time(s1))
+        fl2 = n2 ** 3 / 3.0 + n2 ** 2 / 2.0
+        chol["larger"] = {"n": n2, "ms": best2, "tflops": fl2 / (best2 * 1e-3) / 1e12,
+                          "frac_of_peak": fl2 / (best2 * 1e-3) / 1e12 / peak}
+        del K2, A2, X2
 
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
