@@ -712,7 +712,7 @@ extern "C" int32_t abo_gp_fit(abo_gp* g, const double* X, const double* y, int64
     }
     const int T = (int)(Npad / NB);
     KmatBatch bt{nullptr, nullptr, 0, 0};
-    kmat_kernel<<<dim3(T, T, 1), 256, 0, st>>>(gp_spec(g), g->dXsT, g->ldx, N, g->dL, g->ld, bt);
+    launch_kmat(gp_spec(g), g->dXsT, g->ldx, N, g->dL, g->ld, bt, T, 1, st);
     KL(c);
 
     double* Dinv; int* dinfo; double* W;

@@ -201,7 +201,7 @@ extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, i
             KL(c);
         }
         KmatBatch bt{sb, scb, ldx * d, Npad * Npad};
-        kmat_kernel<<<dim3(T, T, nb), 256, 0, st>>>(spec, Xb, ldx, N, Kb, Npad, bt);
+        launch_kmat(spec, Xb, ldx, N, Kb, Npad, bt, T, nb, st);
         KL(c);
         if ((rc = potrf_blocked(c, Kb, Npad, Npad, Npad * Npad, Dinv, (int64_t)T * NB * NB, dinfo, nb))) return rc;
         if ((rc = trtri_blocked(c, Kb, Linv, W, Npad, Npad, Npad * Npad, Dinv, (int64_t)T * NB * NB, nb))) return rc;
@@ -214,7 +214,7 @@ extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, i
             if (Npad >= ws_min_n()) CU((launch_gemm_ws<MC, MC>(q, nb, st, c->sms)));
             else CU((launch_gemm<MC, MC, EPI_STORE>(q, nb, st)));
             KL(c);
-            nlml_grad_tile_kernel<<<dim3(T, T, nb), 256, 0, st>>>(spec, bt, Xb, ldx, N, W, Npad, Npad * Npad, alpha, Npad, tpart);
+            launch_nlml_grad(spec, bt, Xb, ldx, N, W, Npad, Npad * Npad, alpha, Npad, tpart, T, nb, st);
             KL(c);
         } else {
             CU(cudaMemsetAsync(tpart, 0, sizeof(double) * (size_t)nb * T * T * 2, st));

@@ -128,6 +128,64 @@ __global__ void __launch_bounds__(256) kmat_kernel(KSpec spec, const double* __r
     }
 }
 
+// scalar GP (p = 1), d <= DT: the same tile with the coordinates in registers / shared memory.  A thread owns CPT
+// columns (x_j in registers) and walks the rows of its row group (x_i broadcast from shared memory), so one shared
+// load feeds CPT distance terms and there is no index arithmetic in the entry loop.  Bit-identical to kmat_kernel
+// (same k order; the zero padding of the coordinates adds exact zeros).
+template <int DT, int CPT>
+__global__ void __launch_bounds__(256) kmat_p1_kernel(KSpec spec, const double* __restrict__ XsT, int64_t ldx, int64_t N,
+                                                      double* __restrict__ Kmat, int64_t ld, KmatBatch bt) {
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    if (bt.s) { spec.s = bt.s[blockIdx.z]; spec.scale = bt.scale[blockIdx.z]; }
+    const double* X = XsT + (int64_t)blockIdx.z * bt.strideX;
+    double* Kb = Kmat + (int64_t)blockIdx.z * bt.strideK;
+    __shared__ double sxi[DT][NB];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < DT * NB; e += 256) {
+        const int k = e >> 7, r = e & 127;
+        const int64_t gr = (int64_t)bi * NB + r;
+        sxi[k][r] = (k < spec.d && gr < N) ? X[k * ldx + gr] : 0.0;
+    }
+    constexpr int TPG = NB / CPT, NG = 256 / TPG, RPG = NB / NG;
+    const int tg = tid % TPG, grp = tid / TPG;
+    double xj[CPT][DT];
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+        const int64_t gc = (int64_t)bj * NB + tg + q * TPG;
+#pragma unroll
+        for (int k = 0; k < DT; ++k) xj[q][k] = (k < spec.d && gc < N) ? X[k * ldx + gc] : 0.0;
+    }
+    __syncthreads();
+    for (int rr = 0; rr < RPG; ++rr) {
+        const int r = grp * RPG + rr;
+        const int64_t gr = (int64_t)bi * NB + r;
+        double u[CPT];
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) u[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            const double xi = sxi[k][r];
+#pragma unroll
+            for (int q = 0; q < CPT; ++q) { const double df = xi - xj[q][k]; u[q] = fma(df, df, u[q]); }
+        }
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) {
+            const int64_t gc = (int64_t)bj * NB + tg + q * TPG;
+            double v;
+            if (gr >= N || gc >= N) {
+                v = (gr == gc) ? 1.0 : 0.0;
+            } else {
+                double p, dp, ddp;
+                phi_eval(spec.kind, u[q], p, dp, ddp);
+                v = spec.scale * p;
+                if (gr == gc) v += spec.noise;
+            }
+            Kb[gr * ld + gc] = v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // 128 x 128 diagonal block of the blocked Cholesky:  A = L L^T in shared memory and L^-1 of the
 // block.  Writes L (upper part zeroed) back in place and L^-1 to Dinv.  A non-positive pivot
@@ -842,6 +900,108 @@ __global__ void __launch_bounds__(256) nlml_grad_tile_kernel(KSpec spec, KmatBat
         o[0] = sh[0][0]; o[1] = sh[1][0];
     }
 }
+// scalar GP (p = 1), d <= DT: register/shared-memory tiling as kmat_p1_kernel
+template <int DT, int CPT>
+__global__ void __launch_bounds__(256) nlml_grad_p1_kernel(KSpec spec, KmatBatch bt, const double* __restrict__ XsT,
+                                                           int64_t ldx, int64_t N, const double* __restrict__ Cinv,
+                                                           int64_t ld, int64_t strideC, const double* __restrict__ alpha,
+                                                           int64_t strideV, double* __restrict__ part) {
+    __shared__ double sxi[DT][NB];
+    __shared__ double sal[NB];
+    __shared__ double sh[2][256];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    const int T = gridDim.x;
+    const int tid = threadIdx.x;
+    double g0 = 0.0, g1 = 0.0;
+    if (bj <= bi) {
+        spec.s = bt.s[blockIdx.z]; spec.scale = bt.scale[blockIdx.z];
+        const double* X = XsT + (int64_t)blockIdx.z * bt.strideX;
+        const double* Cb = Cinv + (int64_t)blockIdx.z * strideC;
+        const double* al = alpha + (int64_t)blockIdx.z * strideV;
+        for (int e = tid; e < DT * NB; e += 256) {
+            const int k = e >> 7, r = e & 127;
+            const int64_t gr = (int64_t)bi * NB + r;
+            sxi[k][r] = (k < spec.d && gr < N) ? X[k * ldx + gr] : 0.0;
+        }
+        if (tid < NB) { const int64_t gr = (int64_t)bi * NB + tid; sal[tid] = gr < N ? al[gr] : 0.0; }
+        constexpr int TPG = NB / CPT, NG = 256 / TPG, RPG = NB / NG;
+        const int tg = tid % TPG, grp = tid / TPG;
+        double xj[CPT][DT], alc[CPT];
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) {
+            const int64_t gc = (int64_t)bj * NB + tg + q * TPG;
+            alc[q] = gc < N ? al[gc] : 0.0;
+#pragma unroll
+            for (int k = 0; k < DT; ++k) xj[q][k] = (k < spec.d && gc < N) ? X[k * ldx + gc] : 0.0;
+        }
+        __syncthreads();
+        for (int rr = 0; rr < RPG; ++rr) {
+            const int r = grp * RPG + rr;
+            const int64_t gr = (int64_t)bi * NB + r;
+            if (gr >= N) continue;
+            double u[CPT];
+#pragma unroll
+            for (int q = 0; q < CPT; ++q) u[q] = 0.0;
+#pragma unroll
+            for (int k = 0; k < DT; ++k) {
+                const double xi = sxi[k][r];
+#pragma unroll
+                for (int q = 0; q < CPT; ++q) { const double df = xi - xj[q][k]; u[q] = fma(df, df, u[q]); }
+            }
+            const double alr = sal[r];
+#pragma unroll
+            for (int q = 0; q < CPT; ++q) {
+                const int64_t gc = (int64_t)bj * NB + tg + q * TPG;
+                if (gc >= N || gc > gr) continue;
+                double p, dp, ddp;
+                phi_eval(spec.kind, u[q], p, dp, ddp);
+                const double kv = spec.scale * p;
+                const double dk = -2.0 * spec.scale * dp * u[q];
+                const double m = (Cb[gr * ld + gc] - alr * alc[q]) * (gr == gc ? 1.0 : 2.0);
+                g0 = fma(m, dk, g0);
+                g1 = fma(m, kv, g1);
+            }
+        }
+    }
+    sh[0][tid] = g0; sh[1][tid] = g1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) { sh[0][tid] += sh[0][tid + o]; sh[1][tid] += sh[1][tid + o]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double* o = part + ((int64_t)blockIdx.z * T * T + (int64_t)bi * T + bj) * 2;
+        o[0] = sh[0][0]; o[1] = sh[1][0];
+    }
+}
+
+// dispatch on d: scalar GPs with d <= 32 take the tiled kernels, everything else the generic ones
+inline void launch_kmat(const KSpec& spec, const double* XsT, int64_t ldx, int64_t N, double* K, int64_t ld, const KmatBatch& bt,
+                        int T, int batch, cudaStream_t st) {
+    const dim3 grid(T, T, batch);
+    if (spec.p == 1 && spec.d <= 4) kmat_p1_kernel<4, 4><<<grid, 256, 0, st>>>(spec, XsT, ldx, N, K, ld, bt);
+    else if (spec.p == 1 && spec.d <= 8) kmat_p1_kernel<8, 4><<<grid, 256, 0, st>>>(spec, XsT, ldx, N, K, ld, bt);
+    else if (spec.p == 1 && spec.d <= 12) kmat_p1_kernel<12, 2><<<grid, 256, 0, st>>>(spec, XsT, ldx, N, K, ld, bt);
+    else if (spec.p == 1 && spec.d <= 16) kmat_p1_kernel<16, 2><<<grid, 256, 0, st>>>(spec, XsT, ldx, N, K, ld, bt);
+    else if (spec.p == 1 && spec.d <= 20) kmat_p1_kernel<20, 2><<<grid, 256, 0, st>>>(spec, XsT, ldx, N, K, ld, bt);
+    else if (spec.p == 1 && spec.d <= 32) kmat_p1_kernel<32, 1><<<grid, 256, 0, st>>>(spec, XsT, ldx, N, K, ld, bt);
+    else kmat_kernel<<<grid, 256, 0, st>>>(spec, XsT, ldx, N, K, ld, bt);
+}
+inline void launch_nlml_grad(const KSpec& spec, const KmatBatch& bt, const double* XsT, int64_t ldx, int64_t N, const double* Cinv,
+                             int64_t ld, int64_t strideC, const double* alpha, int64_t strideV, double* part, int T, int batch,
+                             cudaStream_t st) {
+    const dim3 grid(T, T, batch);
+#define ABO_NG(DT, CPT) nlml_grad_p1_kernel<DT, CPT><<<grid, 256, 0, st>>>(spec, bt, XsT, ldx, N, Cinv, ld, strideC, alpha, strideV, part)
+    if (spec.p == 1 && spec.d <= 4) ABO_NG(4, 4);
+    else if (spec.p == 1 && spec.d <= 8) ABO_NG(8, 4);
+    else if (spec.p == 1 && spec.d <= 12) ABO_NG(12, 2);
+    else if (spec.p == 1 && spec.d <= 16) ABO_NG(16, 2);
+    else if (spec.p == 1 && spec.d <= 20) ABO_NG(20, 2);
+    else if (spec.p == 1 && spec.d <= 32) ABO_NG(32, 1);
+    else nlml_grad_tile_kernel<<<grid, 256, 0, st>>>(spec, bt, XsT, ldx, N, Cinv, ld, strideC, alpha, strideV, part);
+#undef ABO_NG
+}
+
 // one block per batch: nlml = (N log 2pi + 2 sum log L_ii + ||beta||^2) / 2, grad = (sum of tile partials) / 2
 __global__ void __launch_bounds__(256) nlml_finish_kernel(const double* __restrict__ L, int64_t ld, int64_t strideM, int64_t N,
                                                           const double* __restrict__ beta, int64_t strideV,
