@@ -902,7 +902,7 @@ __global__ void __launch_bounds__(256) nlml_grad_tile_kernel(KSpec spec, KmatBat
 }
 // scalar GP (p = 1), d <= DT: register/shared-memory tiling as kmat_p1_kernel
 template <int DT, int CPT>
-__global__ void __launch_bounds__(256) nlml_grad_p1_kernel(KSpec spec, KmatBatch bt, const double* __restrict__ XsT,
+__global__ void __launch_bounds__(256, 2) nlml_grad_p1_kernel(KSpec spec, KmatBatch bt, const double* __restrict__ XsT,
                                                            int64_t ldx, int64_t N, const double* __restrict__ Cinv,
                                                            int64_t ld, int64_t strideC, const double* __restrict__ alpha,
                                                            int64_t strideV, double* __restrict__ part) {
@@ -935,31 +935,44 @@ __global__ void __launch_bounds__(256) nlml_grad_p1_kernel(KSpec spec, KmatBatch
             for (int k = 0; k < DT; ++k) xj[q][k] = (k < spec.d && gc < N) ? X[k * ldx + gc] : 0.0;
         }
         __syncthreads();
-        for (int rr = 0; rr < RPG; ++rr) {
-            const int r = grp * RPG + rr;
-            const int64_t gr = (int64_t)bi * NB + r;
-            if (gr >= N) continue;
-            double u[CPT];
+        constexpr int RB = 4;                              // rows per batch: their Cinv loads are issued together
+        for (int rr0 = 0; rr0 < RPG; rr0 += RB) {
+            double cv[RB][CPT];
 #pragma unroll
-            for (int q = 0; q < CPT; ++q) u[q] = 0.0;
+            for (int i = 0; i < RB; ++i) {
+                const int64_t gr = (int64_t)bi * NB + grp * RPG + rr0 + i;
 #pragma unroll
-            for (int k = 0; k < DT; ++k) {
-                const double xi = sxi[k][r];
-#pragma unroll
-                for (int q = 0; q < CPT; ++q) { const double df = xi - xj[q][k]; u[q] = fma(df, df, u[q]); }
+                for (int q = 0; q < CPT; ++q) {
+                    const int64_t gc = (int64_t)bj * NB + tg + q * TPG;
+                    cv[i][q] = (gr < N && gc <= gr) ? __ldg(Cb + gr * ld + gc) : 0.0;
+                }
             }
-            const double alr = sal[r];
 #pragma unroll
-            for (int q = 0; q < CPT; ++q) {
-                const int64_t gc = (int64_t)bj * NB + tg + q * TPG;
-                if (gc >= N || gc > gr) continue;
-                double p, dp, ddp;
-                phi_eval(spec.kind, u[q], p, dp, ddp);
-                const double kv = spec.scale * p;
-                const double dk = -2.0 * spec.scale * dp * u[q];
-                const double m = (Cb[gr * ld + gc] - alr * alc[q]) * (gr == gc ? 1.0 : 2.0);
-                g0 = fma(m, dk, g0);
-                g1 = fma(m, kv, g1);
+            for (int i = 0; i < RB; ++i) {
+                const int r = grp * RPG + rr0 + i;
+                const int64_t gr = (int64_t)bi * NB + r;
+                double u[CPT];
+#pragma unroll
+                for (int q = 0; q < CPT; ++q) u[q] = 0.0;
+#pragma unroll
+                for (int k = 0; k < DT; ++k) {
+                    const double xi = sxi[k][r];
+#pragma unroll
+                    for (int q = 0; q < CPT; ++q) { const double df = xi - xj[q][k]; u[q] = fma(df, df, u[q]); }
+                }
+                const double alr = sal[r];
+#pragma unroll
+                for (int q = 0; q < CPT; ++q) {
+                    const int64_t gc = (int64_t)bj * NB + tg + q * TPG;
+                    const bool valid = gr < N && gc <= gr;
+                    double p, dp, ddp;
+                    phi_eval(spec.kind, u[q], p, dp, ddp);
+                    const double kv = spec.scale * p;
+                    const double dk = -2.0 * spec.scale * dp * u[q];
+                    const double m = valid ? (cv[i][q] - alr * alc[q]) * (gr == gc ? 1.0 : 2.0) : 0.0;
+                    g0 = fma(m, dk, g0);
+                    g1 = fma(m, kv, g1);
+                }
             }
         }
     }
