@@ -87,6 +87,8 @@ extern "C" int32_t abo_ctx_create(int32_t device, abo_ctx** out) {
     for (int q = 0; q < 2; ++q) {
         CU(cudaEventCreateWithFlags(&c->ev_ks[q], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_sw[q], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_h2d[q], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_pc[q], cudaEventDisableTiming));
     }
     int rc = configure_kernels();
     if (rc) return rc;
@@ -105,7 +107,7 @@ extern "C" int32_t abo_ctx_destroy(abo_ctx* c) {
     abo_nccl_teardown(c);
     cudaEventDestroy(c->ev_a);
     cudaEventDestroy(c->ev_b);
-    for (int q = 0; q < 2; ++q) { cudaEventDestroy(c->ev_ks[q]); cudaEventDestroy(c->ev_sw[q]); }
+    for (int q = 0; q < 2; ++q) { cudaEventDestroy(c->ev_ks[q]); cudaEventDestroy(c->ev_sw[q]); cudaEventDestroy(c->ev_h2d[q]); cudaEventDestroy(c->ev_pc[q]); }
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream3);
@@ -1132,8 +1134,50 @@ extern "C" int32_t abo_acq_eval(abo_gp* g, int32_t acq_id, const double* params,
     CU(cudaSetDevice(c->device));
     double* dXc;
     if ((rc = ws_get(c, WS_CAND, sizeof(double) * (size_t)m * g->d, (void**)&dXc))) return rc;
-    CU(cudaMemcpyAsync(dXc, Xc, sizeof(double) * m * g->d, cudaMemcpyHostToDevice, c->stream));
-    return acq_eval_common(g, acq_id, params, dXc, m, nullptr, scores, k, top_idx, top_val);
+    static const int64_t piece = getenv("ABO_ACQ_PIECE") ? atoll(getenv("ABO_ACQ_PIECE")) : 262144;
+    if (m <= piece || c->profile) {
+        CU(cudaMemcpyAsync(dXc, Xc, sizeof(double) * m * g->d, cudaMemcpyHostToDevice, c->stream));
+        return acq_eval_common(g, acq_id, params, dXc, m, nullptr, scores, k, top_idx, top_val);
+    }
+    // Large host candidate sets go through in pieces so that the copies hide behind the sweep: while piece i
+    // is being evaluated the host stages piece i+1 (H2D on the copy stream), then reads back the scores of
+    // piece i-1 and feeds them to the top-k heap.  Per-candidate results do not depend on the piece size.
+    cudaStream_t st = c->stream, sc = c->stream3;
+    const int d = g->d;
+    const int64_t np = (m + piece - 1) / piece;
+    double* dS;
+    if ((rc = ws_get(c, WS_OUT_A, sizeof(double) * (size_t)m, (void**)&dS))) return rc;
+    const bool want_host = scores || k > 0;
+    double* hs = scores;
+    if (want_host && !hs) { if ((rc = pinned_get(c, sizeof(double) * (size_t)m, (void**)&hs))) return rc; }
+    std::vector<std::pair<uint64_t, int64_t>> heap;
+    if (k > 0) heap.reserve((size_t)std::min(k, m) + 1);
+    auto off = [&](int64_t i) { return i * piece; };
+    auto cnt = [&](int64_t i) { return std::min(piece, m - i * piece); };
+    auto drain = [&](int64_t i) -> int {                 // scores of piece i -> host, top-k heap
+        if (!want_host) return ABO_OK;
+        CU(cudaStreamWaitEvent(sc, c->ev_pc[i & 1], 0));
+        CU(cudaMemcpyAsync(hs + off(i), dS + off(i), sizeof(double) * cnt(i), cudaMemcpyDeviceToHost, sc));
+        CU(cudaStreamSynchronize(sc));
+        if (k > 0) topk_host(hs + off(i), cnt(i), std::min(k, m), off(i), heap);
+        return ABO_OK;
+    };
+    CU(cudaMemcpyAsync(dXc, Xc, sizeof(double) * cnt(0) * d, cudaMemcpyHostToDevice, sc));
+    CU(cudaEventRecord(c->ev_h2d[0], sc));
+    for (int64_t i = 0; i < np; ++i) {
+        CU(cudaStreamWaitEvent(st, c->ev_h2d[i & 1], 0));
+        if ((rc = sweep_device(g, dXc + off(i) * d, cnt(i), 0, acq_id, params, nullptr, nullptr, dS + off(i)))) return rc;
+        CU(cudaEventRecord(c->ev_pc[i & 1], st));
+        if (i + 1 < np) {
+            CU(cudaMemcpyAsync(dXc + off(i + 1) * d, Xc + off(i + 1) * d, sizeof(double) * cnt(i + 1) * d, cudaMemcpyHostToDevice, sc));
+            CU(cudaEventRecord(c->ev_h2d[(i + 1) & 1], sc));
+        }
+        if (i >= 1 && (rc = drain(i - 1))) return rc;
+    }
+    if ((rc = drain(np - 1))) return rc;
+    CU(cudaStreamSynchronize(st));
+    if (k > 0) topk_finish(heap, hs, 0, top_idx, top_val);
+    return ABO_OK;
 }
 
 extern "C" int32_t abo_acq_eval_dev(abo_gp* g, int32_t acq_id, const double* params, const double* d_Xc, int64_t m,
