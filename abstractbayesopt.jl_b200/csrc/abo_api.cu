@@ -793,6 +793,23 @@ static void launch_ks(abo_ctx* c, const abo_gp* g, const double* dXc, int64_t c_
             gp_spec(g), g->dXsT, g->ldx, g->n, g->N, g->Npad, g->dAlpha, dXc, c_begin, m_total, bo, Ks, pmean, mc);
 }
 
+static int launch_ks_d(abo_ctx* c, const abo_gp* g, const double* dXc, int64_t c0, int64_t m, int bo, double* Ks, double* pmean,
+                       int64_t mc_eff, int64_t mc, int npb, cudaStream_t st) {
+    const int d = g->d;
+    if (d <= 4) launch_ks<4>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, st);
+    else if (d <= 8) launch_ks<8>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, st);
+    else if (d <= 12) launch_ks<12>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, st);
+    else if (d <= 16) launch_ks<16>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, st);
+    else if (d <= 20) launch_ks<20>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, st);
+    else if (d <= 24) launch_ks<24>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, st);
+    else if (d <= 32) launch_ks<32>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, st);
+    else
+        ks_build_generic_kernel<<<dim3(npb, (unsigned)(mc_eff / KS_CB)), 128, 0, st>>>(
+            gp_spec(g), g->dXsT, g->ldx, g->n, g->N, g->Npad, g->dAlpha, dXc, c0, m, bo, Ks, pmean, mc);
+    KL(c);
+    return ABO_OK;
+}
+
 static double phi_prime0(int kind) {
     if (kind == K_SE) return -0.5;
     if (kind == K_M52 || kind == K_AM52 || kind == K_ADM52) return -5.0 / 6.0;

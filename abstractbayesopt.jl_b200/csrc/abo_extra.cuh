@@ -76,11 +76,131 @@ static int grow_points(abo_gp* g) {
     return ABO_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// block append for a GradientGP: the p = d + 1 outputs of ONE new point become the last p rows of
+// the (point-major) system.
+//   Kn = K((X, all outputs), (x, b)), b < p       (K* builder, one output at a time)
+//   W  = L^-1 Kn ,  S = Knn + noise I - W^T W  ->  host Cholesky S = LS LS^T (p x p; failure leaves the
+//   posterior untouched),  Z = L^-T W
+//   L_new = [[L, 0], [W^T, LS]] ,  Linv_new = [[Linv, 0], [-LS^-1 Z^T, LS^-1]]
+//   beta_new = LS^-1 (delta_new - W^T beta) ,  alpha = [alpha - Z gamma ; gamma],  gamma = LS^-T beta_new
+// O(N^2 p) instead of the O(N^3) re-fit of GradientGP.jl:659-668.
+// ------------------------------------------------------------------------------------------
+static int append_block(abo_gp* g, const double* x, const double* y, int64_t* info_out) {
+    abo_ctx* c = g->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int p = g->p, d = g->d;
+    if (p > 96) return abo_fail(ABO_ERR_INVALID, "block append supports p <= 96");
+    const int64_t N = g->N, Npad = g->Npad;
+    const int64_t vpts = (Npad + p - 1) / p;
+    const int npb = (int)((vpts + 127) / 128);
+    const int64_t WB = NB;                                    // padded width of the p-column operands
+    int rc;
+    double *dx, *Ks, *pmean, *W, *Z, *G, *dsmall;
+    if ((rc = ws_get(c, WS_CAND, sizeof(double) * (size_t)d, (void**)&dx))) return rc;
+    if ((rc = ws_get(c, WS_KS, sizeof(double) * (size_t)WB * Npad, (void**)&Ks))) return rc;
+    if ((rc = ws_get(c, WS_PMEAN, sizeof(double) * (size_t)npb * WB, (void**)&pmean))) return rc;
+    if ((rc = ws_get(c, WS_GRAD_W, sizeof(double) * (size_t)WB * Npad, (void**)&W))) return rc;
+    if ((rc = ws_get(c, WS_GRAD_Z, sizeof(double) * (size_t)WB * Npad, (void**)&Z))) return rc;
+    if ((rc = ws_get(c, WS_GRAD_OUT, sizeof(double) * (size_t)WB * WB, (void**)&G))) return rc;
+    const int nsmall = 2 * p * p + 3 * p + d;
+    if ((rc = ws_get(c, WS_APPEND, sizeof(double) * (size_t)(nsmall + p * p + p + 8), (void**)&dsmall))) return rc;
+    double* dstats = dsmall + nsmall;                          // S | wb
+    CU(cudaMemcpyAsync(dx, x, sizeof(double) * d, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(Ks, 0, sizeof(double) * (size_t)WB * Npad, st));
+    // row b of Ks = column b of Kn; every launch also zeroes the 31 rows after its own, later launches overwrite them
+    for (int b = 0; b < p; ++b)
+        if ((rc = launch_ks_d(c, g, dx, 0, 1, b, Ks + (size_t)b * Npad, pmean, KS_CB, WB, npb, st))) return rc;
+    GemmParams w{};                                            // W = L^-1 Kn      [Npad][WB]
+    w.A = g->dLinv; w.lda = g->ld; w.B = Ks; w.ldb = Npad; w.C = W; w.ldc = WB;
+    w.M = (int)Npad; w.N = (int)WB; w.K = (int)Npad; w.alpha = 1.0; w.beta = 0.0; w.flags = KHI_M;
+    CU((launch_gemm<KC, KC, EPI_STORE>(w, 1, st)));
+    KL(c);
+    GemmParams q{};                                            // G = W^T W
+    q.A = W; q.lda = WB; q.B = W; q.ldb = WB; q.C = G; q.ldc = WB;
+    q.M = (int)WB; q.N = (int)WB; q.K = (int)Npad; q.alpha = 1.0; q.beta = 0.0; q.flags = 0;
+    CU((launch_gemm<MC, MC, EPI_STORE>(q, 1, st)));
+    KL(c);
+    append_block_stats_kernel<<<1, 256, 0, st>>>(spec_of(g), G, WB, W, WB, g->dBeta, N, dstats);
+    KL(c);
+    std::vector<double> hs((size_t)p * p + p);
+    CU(cudaMemcpyAsync(hs.data(), dstats, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost, st));
+    GemmParams z{};                                            // Z = L^-T W, launched now so that it overlaps the host Cholesky
+    z.A = g->dLinv; z.lda = g->ld; z.B = W; z.ldb = WB; z.C = Z; z.ldc = WB;
+    z.M = (int)Npad; z.N = (int)WB; z.K = (int)Npad; z.alpha = 1.0; z.beta = 0.0; z.flags = KLO_M;
+    CU(cudaEventRecord(c->ev_a, st));
+    CU((launch_gemm<MC, MC, EPI_STORE>(z, 1, st)));
+    KL(c);
+    CU(cudaEventSynchronize(c->ev_a));                         // S and wb are on the host; Z is still being computed
+    // host: Cholesky of S, its inverse, beta_new, gamma
+    std::vector<double> small((size_t)nsmall, 0.0);
+    double* LS = small.data(); double* LSi = LS + p * p; double* bnew = LSi + p * p; double* gamma = bnew + p;
+    double* dnew = gamma + p; double* hx = dnew + p;
+    const double* S = hs.data(); const double* wb = S + p * p;
+    for (int a = 0; a < p; ++a) {
+        for (int b = 0; b <= a; ++b) {
+            double v = S[a * p + b];
+            for (int k = 0; k < b; ++k) v -= LS[a * p + k] * LS[b * p + k];
+            if (a == b) {
+                if (!(v > 0.0)) {
+                    if (info_out) *info_out = N + a + 1;
+                    return abo_fail(ABO_ERR_NOT_POSDEF, "matrix is not positive definite; Cholesky factorization failed at pivot %lld",
+                                    (long long)(N + a + 1));
+                }
+                LS[a * p + a] = std::sqrt(v);
+            } else {
+                LS[a * p + b] = v / LS[b * p + b];
+            }
+        }
+    }
+    if (info_out) *info_out = 0;
+    for (int j = 0; j < p; ++j) {                              // LSi = LS^-1 (lower), column by column
+        LSi[j * p + j] = 1.0 / LS[j * p + j];
+        for (int a = j + 1; a < p; ++a) {
+            double v = 0.0;
+            for (int k = j; k < a; ++k) v -= LS[a * p + k] * LSi[k * p + j];
+            LSi[a * p + j] = v / LS[a * p + a];
+        }
+    }
+    for (int a = 0; a < p; ++a) dnew[a] = y[a] - g->mean_c[a];
+    for (int a = 0; a < p; ++a) {
+        double v = 0.0;
+        for (int b = 0; b <= a; ++b) v += LSi[a * p + b] * (dnew[b] - wb[b]);
+        bnew[a] = v;
+    }
+    for (int a = 0; a < p; ++a) {
+        double v = 0.0;
+        for (int b = a; b < p; ++b) v += LSi[b * p + a] * bnew[b];
+        gamma[a] = v;
+    }
+    for (int k = 0; k < d; ++k) hx[k] = x[k];
+    if ((rc = gp_unshare(g))) return rc;                       // copy-on-write: clones keep the un-appended posterior
+    while (N + p > g->cap_pad) { if ((rc = grow_capacity(g))) return rc; }
+    if (g->n + 1 > g->ldx) { if ((rc = grow_points(g))) return rc; }
+    CU(cudaMemcpyAsync(dsmall, small.data(), sizeof(double) * nsmall, cudaMemcpyHostToDevice, st));
+    append_block_commit_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(g->dL, g->dLinv, g->ld, N, p, W, Z, WB, dsmall, g->dDelta,
+                                                                           g->dBeta, g->dAlpha, g->dXsT, g->ldx, g->n, d, g->s);
+    KL(c);
+    CU(cudaStreamSynchronize(st));
+    g->n += 1; g->N += p;
+    g->hX.insert(g->hX.end(), x, x + d);
+    {   // host copy of y is out-major [output][point]: re-interleave with the new point
+        const int64_t n_old = g->n - 1;
+        std::vector<double> ny((size_t)g->N);
+        for (int a = 0; a < p; ++a) {
+            for (int64_t i = 0; i < n_old; ++i) ny[(size_t)a * g->n + i] = g->hY[(size_t)a * n_old + i];
+            ny[(size_t)a * g->n + n_old] = y[a];
+        }
+        g->hY.swap(ny);
+    }
+    return ABO_OK;
+}
+
 extern "C" int32_t abo_gp_append(abo_gp* g, const double* x, const double* y, int64_t* info_out) {
     if (!g || !x || !y) return abo_fail(ABO_ERR_INVALID, "null argument");
     if (!g->fitted) return abo_fail(ABO_ERR_NOT_FITTED, "append needs a fitted surrogate (call abo_gp_fit first)");
-    if (g->p != 1)
-        return abo_fail(ABO_ERR_INVALID, "abo_gp_append supports StandardGP (p = 1); re-fit a GradientGP");
+    if (g->p != 1) return append_block(g, x, y, info_out);
     abo_ctx* c = g->ctx;
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;

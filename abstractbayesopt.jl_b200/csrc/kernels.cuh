@@ -803,6 +803,75 @@ __global__ void __launch_bounds__(1024) append_commit_kernel(double* __restrict_
     for (int64_t j = threadIdx.x; j < n; j += 1024) alpha[j] = fma(Linv[n * ld + j], bn, alpha[j]);
     for (int k = threadIdx.x; k < d; k += 1024) XsT[k * ldx + n] = s * xnew[k];
 }
+// ---- block append of the p outputs of one new point (GradientGP) ------------------------------------
+// W = L^-1 Kn  [Npad][ldw], G = W^T W [..][ldg].  out = S (p x p, row-major) | wb (p):
+//   S = Knn + noise I - W^T W   (Knn: gradKernel of the point with itself, closed form at u = 0)
+//   wb = W^T beta
+__global__ void __launch_bounds__(256) append_block_stats_kernel(KSpec spec, const double* __restrict__ G, int64_t ldg,
+                                                                 const double* __restrict__ W, int64_t ldw,
+                                                                 const double* __restrict__ beta, int64_t N,
+                                                                 double* __restrict__ out) {
+    __shared__ double sh[256];
+    const int p = spec.p, tid = threadIdx.x;
+    double ph, dph, ddph;
+    phi_eval(spec.kind, 0.0, ph, dph, ddph);
+    for (int e = tid; e < p * p; e += 256) {
+        const int a = e / p, b = e % p;
+        double knn = gk_entry(spec, ph, dph, ddph, a, b, 0.0, 0.0);
+        if (a == b) knn += spec.noise;
+        out[e] = knn - G[(int64_t)a * ldg + b];
+    }
+    for (int a = 0; a < p; ++a) {
+        double acc = 0.0;
+        for (int64_t k = tid; k < N; k += 256) acc = fma(W[k * ldw + a], beta[k], acc);
+        sh[tid] = acc;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) sh[tid] += sh[tid + o];
+            __syncthreads();
+        }
+        if (tid == 0) out[p * p + a] = sh[0];
+        __syncthreads();
+    }
+}
+// small: LS (p x p) | LSinv (p x p) | beta_new (p) | gamma (p) | delta_new (p) | x (d)   — from the host
+//   L[N+a, :]    = [ W[:, a]^T , LS[a, :a+1] ]
+//   Linv[N+a, :] = [ -(LSinv Z^T)[a, :] , LSinv[a, :a+1] ]
+//   alpha[:N]   -= Z gamma ; alpha[N+a] = gamma[a] ; beta[N+a] = beta_new[a] ; delta[N+a] = delta_new[a]
+__global__ void __launch_bounds__(256) append_block_commit_kernel(double* __restrict__ L, double* __restrict__ Linv, int64_t ld,
+                                                                  int64_t N, int p, const double* __restrict__ W,
+                                                                  const double* __restrict__ Z, int64_t ldw,
+                                                                  const double* __restrict__ small, double* __restrict__ delta,
+                                                                  double* __restrict__ beta, double* __restrict__ alpha,
+                                                                  double* __restrict__ XsT, int64_t ldx, int64_t npts, int d,
+                                                                  double s) {
+    const double* LS = small;
+    const double* LSinv = small + p * p;
+    const double* bnew = LSinv + p * p;
+    const double* gamma = bnew + p;
+    const double* dnew = gamma + p;
+    const double* x = dnew + p;
+    const int64_t k = blockIdx.x * 256LL + threadIdx.x;
+    if (k < N) {
+        double da = 0.0;
+        for (int a = 0; a < p; ++a) {
+            L[(N + a) * ld + k] = W[k * ldw + a];
+            double li = 0.0;
+            for (int b = 0; b <= a; ++b) li = fma(LSinv[a * p + b], Z[k * ldw + b], li);
+            Linv[(N + a) * ld + k] = -li;
+            da = fma(Z[k * ldw + a], gamma[a], da);
+        }
+        alpha[k] -= da;
+    }
+    if (blockIdx.x == 0) {
+        for (int e = threadIdx.x; e < p * p; e += 256) {
+            const int a = e / p, b = e % p;
+            if (b <= a) { L[(N + a) * ld + N + b] = LS[e]; Linv[(N + a) * ld + N + b] = LSinv[e]; }
+        }
+        for (int a = threadIdx.x; a < p; a += 256) { alpha[N + a] = gamma[a]; beta[N + a] = bnew[a]; delta[N + a] = dnew[a]; }
+        for (int q = threadIdx.x; q < d; q += 256) XsT[q * ldx + npts] = s * x[q];
+    }
+}
 // grow a padded lower-triangular matrix: copy the old Npad x Npad block, identity in the new part
 __global__ void grow_matrix_kernel(const double* __restrict__ src, int64_t old_pad, int64_t old_ld,
                                    double* __restrict__ dst, int64_t new_pad) {

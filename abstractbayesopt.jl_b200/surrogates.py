@@ -120,7 +120,8 @@ def update_surrogate(model, xs, ys, allow_append=True):
     conditioned on (xs, ys); raises PosDefException when the Cholesky fails (the BO loop catches
     it, src/bayesian_opt.jl:126-141) and DimensionMismatch on inconsistent inputs.
     When (xs, ys) extends the data the model already holds by exactly one observation the
-    O(n²) row append (abo_gp_append) is used on a copy instead of the O(n³) re-fit."""
+    O(n²) row append (abo_gp_append; p rows at once for a GradientGP) is used on a copy-on-write
+    clone instead of the O(n³) re-fit."""
     X = _as_points(xs)
     n, d = X.shape
     if isinstance(model, GradientGP) and model.p != d + 1:
@@ -130,12 +131,13 @@ def update_surrogate(model, xs, ys, allow_append=True):
     old = model.gpx
     if old is not None and old.d != d:
         raise DimensionMismatch(f"points have dimension {d}, the surrogate was conditioned on dimension {old.d}")
-    if (allow_append and old is not None and model._data is not None and model.p == 1
+    pp = model.p
+    if (allow_append and old is not None and model._data is not None
             and model._data[0].shape[0] == n - 1 and np.array_equal(model._data[0], X[:-1])
-            and np.array_equal(model._data[1], y[:-1])):
-        h = old.clone()
+            and np.array_equal(model._data[1].reshape(pp, n - 1), y.reshape(pp, n)[:, :-1])):
+        h = old.clone()                                  # O(1): copy-on-write handle
         try:
-            h.append(X[-1], y[-1:])
+            h.append(X[-1], y.reshape(pp, n)[:, -1])     # out-major y: the new point's p outputs
         except Exception:
             h.close()
             raise

@@ -246,6 +246,46 @@ def test_append_is_transactional(abo, orc):
     assert m1[0] == m0[0] and v1[0] == v0[0]
 
 
+@pytest.mark.parametrize("kind,n0,n1,d", [(0, 5, 30, 2), (3, 20, 40, 10), (4, 11, 26, 4)])
+def test_gradient_gp_block_append_matches_refit(abo, orc, kind, n0, n1, d):
+    """GradientGP: appending the p = d + 1 outputs of one point at a time (O(N^2 p)) equals the re-fit the
+    reference does (GradientGP.jl:659-668), across tile boundaries (N crosses 128 / 256 / 384)."""
+    rng = np.random.default_rng(17 * n1 + d)
+    X = -2 + 4 * rng.random((n1, d))
+    Y = orc.rosenbrock_with_grad(X); Y = Y / np.std(Y[:, 0])
+    Xc = -2 + 4 * rng.random((200, d))
+    inv_ls, scale, noise = 1.0 / 1.5, 1.3, 1e-4
+    gp = abo.update(abo.GradientGP(make_kernel(abo, kind, inv_ls, scale), d + 1, noise), X[:n0], Y[:n0])
+    snapshots = []
+    for i in range(n0, n1):
+        prev = gp
+        gp = abo.update(gp, X[:i + 1], Y[:i + 1])
+        assert gp.gpx.n() == i + 1 and prev.gpx.n() == i            # functional update: the old model is untouched
+        if i == n0 + 2:
+            snapshots.append((prev, abo.posterior_mean(prev, Xc[:20]).copy()))
+    post = orc.fit_gradient(X, Y, kind, inv_ls, scale, noise)
+    mu_o, var_o = orc.posterior_mean_var(post, Xc)
+    cond = np.linalg.cond(post.U) ** 2
+    tol = max(RTOL, 200 * cond * 2.2e-16)
+    sc = max(scale, np.max(np.abs(mu_o)))
+    assert close(abo.posterior_mean(gp, Xc), mu_o, sc, tol), cond
+    assert close(abo.posterior_var(gp, Xc), var_o, scale, tol), cond
+    gm_o, gv_o = orc.posterior_mean_var(post, Xc[:40], outputs=range(d + 1))
+    assert close(abo.posterior_grad_mean(gp, Xc[:40]), gm_o, max(sc, np.max(np.abs(gm_o))), tol)
+    assert close(abo.posterior_grad_var(gp, Xc[:40]), gv_o, max(scale, np.max(np.abs(gv_o))), tol)
+    full = abo.update(abo.GradientGP(make_kernel(abo, kind, inv_ls, scale), d + 1, noise), X, Y, allow_append=False)
+    assert close(gp.gpx.alpha(), full.gpx.alpha(), np.max(np.abs(full.gpx.alpha())), tol)
+    for m_old, mu_then in snapshots:                                  # copy-on-write kept the snapshot intact
+        assert np.array_equal(abo.posterior_mean(m_old, Xc[:20]), mu_then)
+    # transactional failure: a duplicate point with zero noise is not positive definite
+    g0 = abo.update(abo.GradientGP(abo.SqExponentialKernel(), d + 1, 0.0), X[:3], Y[:3])
+    h = g0.gpx.clone()
+    with pytest.raises(abo.PosDefException):
+        h.append(X[0], Y[0])
+    assert h.n() == 3
+    assert np.array_equal(h.posterior(Xc[:5])[0], g0.gpx.posterior(Xc[:5])[0])
+
+
 def test_clone_is_copy_on_write(abo, orc):
     """abo_gp_clone shares the device buffers; every writer (append, re-fit, destroy) must leave the
     other holders' posterior bit-identical (value semantics of Base.copy, StandardGP.jl:26)."""
