@@ -112,26 +112,27 @@ static int append_block(abo_gp* g, const double* x, const double* y, int64_t* in
     // row b of Ks = column b of Kn; every launch also zeroes the 31 rows after its own, later launches overwrite them
     for (int b = 0; b < p; ++b)
         if ((rc = launch_ks_d(c, g, dx, 0, 1, b, Ks + (size_t)b * Npad, pmean, KS_CB, WB, npb, st))) return rc;
-    GemmParams w{};                                            // W = L^-1 Kn      [Npad][WB]
-    w.A = g->dLinv; w.lda = g->ld; w.B = Ks; w.ldb = Npad; w.C = W; w.ldc = WB;
-    w.M = (int)Npad; w.N = (int)WB; w.K = (int)Npad; w.alpha = 1.0; w.beta = 0.0; w.flags = KHI_M;
-    CU((launch_gemm<KC, KC, EPI_STORE>(w, 1, st)));
+    // W = L^-1 Kn [N][WB], G = W^T W: p right-hand sides only -> bandwidth-bound passes over the triangle
+    // (128-wide padded GEMM tiles would run on 44 CTAs with k-loops of up to N)
+    const int ngrp = (p + 7) / 8;
+    trmm_skinny_lower_kernel<<<dim3((unsigned)((N * 32 + 255) / 256), ngrp), 256, 0, st>>>(g->dLinv, g->ld, N, Ks, Npad, p, W, WB);
     KL(c);
-    GemmParams q{};                                            // G = W^T W
-    q.A = W; q.lda = WB; q.B = W; q.ldb = WB; q.C = G; q.ldc = WB;
-    q.M = (int)WB; q.N = (int)WB; q.K = (int)Npad; q.alpha = 1.0; q.beta = 0.0; q.flags = 0;
-    CU((launch_gemm<MC, MC, EPI_STORE>(q, 1, st)));
+    gram_skinny_kernel<<<dim3(p, p), 256, 0, st>>>(W, WB, N, G, WB);
     KL(c);
     append_block_stats_kernel<<<1, 256, 0, st>>>(spec_of(g), G, WB, W, WB, g->dBeta, N, dstats);
     KL(c);
     std::vector<double> hs((size_t)p * p + p);
     CU(cudaMemcpyAsync(hs.data(), dstats, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost, st));
-    GemmParams z{};                                            // Z = L^-T W, launched now so that it overlaps the host Cholesky
-    z.A = g->dLinv; z.lda = g->ld; z.B = W; z.ldb = WB; z.C = Z; z.ldc = WB;
-    z.M = (int)Npad; z.N = (int)WB; z.K = (int)Npad; z.alpha = 1.0; z.beta = 0.0; z.flags = KLO_M;
     CU(cudaEventRecord(c->ev_a, st));
-    CU((launch_gemm<MC, MC, EPI_STORE>(z, 1, st)));
-    KL(c);
+    {   // Z = L^-T W, launched now so that it overlaps the host Cholesky
+        const int nchunks = (int)((N + TRMVT_ROWS - 1) / TRMVT_ROWS);
+        double* part;
+        if ((rc = ws_get(c, WS_VEC_PART, sizeof(double) * (size_t)nchunks * p * N, (void**)&part))) return rc;
+        trmmT_skinny_partial_kernel<<<dim3((unsigned)((N + 127) / 128), nchunks, ngrp), 128, 0, st>>>(g->dLinv, g->ld, N, W, WB, p, part);
+        KL(c);
+        trmmT_skinny_reduce_kernel<<<dim3((unsigned)((N + 127) / 128), p), 128, 0, st>>>(part, nchunks, N, p, Z, WB);
+        KL(c);
+    }
     CU(cudaEventSynchronize(c->ev_a));                         // S and wb are on the host; Z is still being computed
     // host: Cholesky of S, its inverse, beta_new, gamma
     std::vector<double> small((size_t)nsmall, 0.0);

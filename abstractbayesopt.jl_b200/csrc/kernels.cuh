@@ -803,6 +803,81 @@ __global__ void __launch_bounds__(1024) append_commit_kernel(double* __restrict_
     for (int64_t j = threadIdx.x; j < n; j += 1024) alpha[j] = fma(Linv[n * ld + j], bn, alpha[j]);
     for (int k = threadIdx.x; k < d; k += 1024) XsT[k * ldx + n] = s * xnew[k];
 }
+// ---- skinny triangular products for a handful of right-hand sides (block append): bandwidth-bound passes over
+//      the triangle instead of 128-wide padded GEMM tiles.  RHS columns are processed 8 at a time (blockIdx.y).
+// W[r][b] = sum_{k <= r} T[r][k] * Bt[b][k]        (Bt: one K-contiguous row per right-hand side), warp per row
+__global__ void trmm_skinny_lower_kernel(const double* __restrict__ T, int64_t ld, int64_t N, const double* __restrict__ Bt,
+                                         int64_t ldb, int nrhs, double* __restrict__ W, int64_t ldw) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= N) return;
+    const int b0 = blockIdx.y * 8;
+    const double* row = T + r * ld;
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+#pragma unroll 4
+    for (int64_t k = lane; k <= r; k += 32) {
+        const double a = row[k];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (b0 + q < nrhs) acc[q] = fma(a, Bt[(int64_t)(b0 + q) * ldb + k], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        if (lane == 0 && b0 + q < nrhs) W[r * ldw + b0 + q] = acc[q];
+    }
+}
+// part[chunk][b][j] = sum_{i in chunk, i >= j} T[i][j] * V[i][b]     (T^T V, two-stage, deterministic)
+__global__ void trmmT_skinny_partial_kernel(const double* __restrict__ T, int64_t ld, int64_t N, const double* __restrict__ V,
+                                            int64_t ldv, int nrhs, double* __restrict__ part) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.y * TRMVT_ROWS;
+    const int b0 = blockIdx.z * 8;
+    if (j >= N) return;
+    int64_t i1 = i0 + TRMVT_ROWS; if (i1 > N) i1 = N;
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+#pragma unroll 4
+    for (int64_t i = (i0 > j ? i0 : j); i < i1; ++i) {
+        const double a = T[i * ld + j];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (b0 + q < nrhs) acc[q] = fma(a, V[i * ldv + b0 + q], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (b0 + q < nrhs) part[((int64_t)blockIdx.y * nrhs + b0 + q) * N + j] = acc[q];
+}
+// Z[j][b] = sum_chunks part[chunk][b][j]
+__global__ void trmmT_skinny_reduce_kernel(const double* __restrict__ part, int nchunks, int64_t N, int nrhs,
+                                           double* __restrict__ Z, int64_t ldz) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (j >= N) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += part[((int64_t)c * nrhs + b) * N + j];
+    Z[j * ldz + b] = s;
+}
+// G[a][b] = sum_k W[k][a] * W[k][b]     one block per (a, b)
+__global__ void __launch_bounds__(256) gram_skinny_kernel(const double* __restrict__ W, int64_t ldw, int64_t N, double* __restrict__ G,
+                                                          int64_t ldg) {
+    __shared__ double sh[256];
+    const int a = blockIdx.y, b = blockIdx.x;
+    double acc = 0.0;
+    for (int64_t k = threadIdx.x; k < N; k += 256) acc = fma(W[k * ldw + a], W[k * ldw + b], acc);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) G[(int64_t)a * ldg + b] = sh[0];
+}
+
 // ---- block append of the p outputs of one new point (GradientGP) ------------------------------------
 // W = L^-1 Kn  [Npad][ldw], G = W^T W [..][ldg].  out = S (p x p, row-major) | wb (p):
 //   S = Knn + noise I - W^T W   (Knn: gradKernel of the point with itself, closed form at u = 0)

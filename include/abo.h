@@ -88,8 +88,9 @@ int32_t abo_gp_set_params(abo_gp* gp, double inv_lengthscale, double scale, doub
  * alpha.  *info = 0, or the 1-based failing pivot in the caller's out-major ordering is NOT
  * guaranteed — only info > 0 is (status ABO_ERR_NOT_POSDEF); the handle is then un-fitted. */
 int32_t abo_gp_fit(abo_gp* gp, const double* X, const double* y, int64_t n, int64_t* info);
-/* O(n^2) row append of one observation (x[d], y[p]); transactional: on ABO_ERR_NOT_POSDEF the
- * handle still holds the previous posterior.  (The reference re-fits: bayesian_opt.jl:125.) */
+/* O(n^2) append of one observation (x[d], y[p]): one row for a StandardGP, the block of p = d+1 rows
+ * for a GradientGP; transactional: on ABO_ERR_NOT_POSDEF the handle still holds the previous
+ * posterior.  (The reference re-fits: bayesian_opt.jl:125.) */
 int32_t abo_gp_append(abo_gp* gp, const double* x, const double* y, int64_t* info);
 /* Base.copy(::StandardGP) (StandardGP.jl:26, surrogates_utils.jl:12-14).  Value semantics of a deep
  * copy at O(1) cost: the clone shares the device buffers (reference counted) and whichever handle
