@@ -922,6 +922,10 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
     return ABO_OK;
 }
 
+static int64_t host_piece();
+static int sweep_host_pieces(abo_gp* g, const double* Xc, int64_t m, int acq_id, const double* params, double* h_mean,
+                             double* h_var, double* h_scores, int64_t k, int64_t* top_idx, double* top_val);
+
 extern "C" int32_t abo_gp_posterior(abo_gp* g, const double* Xc, int64_t m, int32_t outputs, double* mean, double* var) {
     if (!g || !Xc) return abo_fail(ABO_ERR_INVALID, "null argument");
     if (!g->fitted) return abo_fail(ABO_ERR_NOT_FITTED, "surrogate has no posterior (call update first)");
@@ -929,6 +933,8 @@ extern "C" int32_t abo_gp_posterior(abo_gp* g, const double* Xc, int64_t m, int3
     if (m <= 0) return ABO_OK;
     abo_ctx* c = g->ctx;
     CU(cudaSetDevice(c->device));
+    if (outputs == 1 && m > host_piece() && !c->profile)
+        return sweep_host_pieces(g, Xc, m, -1, nullptr, mean, var, nullptr, 0, nullptr, nullptr);
     cudaStream_t st = c->stream;
     double *dXc, *dm, *dv;
     int rc;
@@ -1142,39 +1148,39 @@ static int acq_check(abo_gp* g, int acq_id, const double* params, const void* Xc
     return ABO_OK;
 }
 
-extern "C" int32_t abo_acq_eval(abo_gp* g, int32_t acq_id, const double* params, const double* Xc, int64_t m,
-                                double* scores, int64_t k, int64_t* top_idx, double* top_val) {
-    int rc = acq_check(g, acq_id, params, Xc, m, k, top_idx, top_val);
-    if (rc) return rc;
-    if (m == 0) return ABO_OK;
-    abo_ctx* c = g->ctx;
-    CU(cudaSetDevice(c->device));
-    double* dXc;
-    if ((rc = ws_get(c, WS_CAND, sizeof(double) * (size_t)m * g->d, (void**)&dXc))) return rc;
+// Large host candidate sets go through in pieces so that the copies hide behind the sweep: while piece i
+// is being evaluated the host stages piece i+1 (H2D on the copy stream), then reads back the results of
+// piece i-1 (and feeds the scores to the top-k heap).  Per-candidate results do not depend on the piece size.
+// acq_id < 0: posterior mean / variance of output 0 (h_mean / h_var, each may be NULL).
+static int64_t host_piece() {
     static const int64_t piece = getenv("ABO_ACQ_PIECE") ? atoll(getenv("ABO_ACQ_PIECE")) : 262144;
-    if (m <= piece || c->profile) {
-        CU(cudaMemcpyAsync(dXc, Xc, sizeof(double) * m * g->d, cudaMemcpyHostToDevice, c->stream));
-        return acq_eval_common(g, acq_id, params, dXc, m, nullptr, scores, k, top_idx, top_val);
-    }
-    // Large host candidate sets go through in pieces so that the copies hide behind the sweep: while piece i
-    // is being evaluated the host stages piece i+1 (H2D on the copy stream), then reads back the scores of
-    // piece i-1 and feeds them to the top-k heap.  Per-candidate results do not depend on the piece size.
+    return piece;
+}
+static int sweep_host_pieces(abo_gp* g, const double* Xc, int64_t m, int acq_id, const double* params, double* h_mean,
+                             double* h_var, double* h_scores, int64_t k, int64_t* top_idx, double* top_val) {
+    abo_ctx* c = g->ctx;
     cudaStream_t st = c->stream, sc = c->stream3;
     const int d = g->d;
+    const int64_t piece = host_piece();
     const int64_t np = (m + piece - 1) / piece;
-    double* dS;
-    if ((rc = ws_get(c, WS_OUT_A, sizeof(double) * (size_t)m, (void**)&dS))) return rc;
-    const bool want_host = scores || k > 0;
-    double* hs = scores;
-    if (want_host && !hs) { if ((rc = pinned_get(c, sizeof(double) * (size_t)m, (void**)&hs))) return rc; }
+    int rc;
+    double *dXc, *dA, *dB = nullptr;
+    if ((rc = ws_get(c, WS_CAND, sizeof(double) * (size_t)m * d, (void**)&dXc))) return rc;
+    if ((rc = ws_get(c, WS_OUT_A, sizeof(double) * (size_t)m, (void**)&dA))) return rc;
+    if (acq_id < 0 && (rc = ws_get(c, WS_OUT_B, sizeof(double) * (size_t)m, (void**)&dB))) return rc;
+    double* hs = h_scores;                               // acquisition: dA = scores; posterior: dA = mean, dB = variance
+    if (acq_id >= 0 && k > 0 && !hs) { if ((rc = pinned_get(c, sizeof(double) * (size_t)m, (void**)&hs))) return rc; }
     std::vector<std::pair<uint64_t, int64_t>> heap;
     if (k > 0) heap.reserve((size_t)std::min(k, m) + 1);
     auto off = [&](int64_t i) { return i * piece; };
     auto cnt = [&](int64_t i) { return std::min(piece, m - i * piece); };
-    auto drain = [&](int64_t i) -> int {                 // scores of piece i -> host, top-k heap
-        if (!want_host) return ABO_OK;
+    auto drain = [&](int64_t i) -> int {                 // results of piece i -> host, top-k heap
+        double* hosts[2] = {acq_id >= 0 ? hs : h_mean, acq_id >= 0 ? nullptr : h_var};
+        double* devs[2] = {dA, dB};
+        if (!hosts[0] && !hosts[1]) return ABO_OK;
         CU(cudaStreamWaitEvent(sc, c->ev_pc[i & 1], 0));
-        CU(cudaMemcpyAsync(hs + off(i), dS + off(i), sizeof(double) * cnt(i), cudaMemcpyDeviceToHost, sc));
+        for (int q = 0; q < 2; ++q)
+            if (hosts[q]) CU(cudaMemcpyAsync(hosts[q] + off(i), devs[q] + off(i), sizeof(double) * cnt(i), cudaMemcpyDeviceToHost, sc));
         CU(cudaStreamSynchronize(sc));
         if (k > 0) topk_host(hs + off(i), cnt(i), std::min(k, m), off(i), heap);
         return ABO_OK;
@@ -1183,7 +1189,9 @@ extern "C" int32_t abo_acq_eval(abo_gp* g, int32_t acq_id, const double* params,
     CU(cudaEventRecord(c->ev_h2d[0], sc));
     for (int64_t i = 0; i < np; ++i) {
         CU(cudaStreamWaitEvent(st, c->ev_h2d[i & 1], 0));
-        if ((rc = sweep_device(g, dXc + off(i) * d, cnt(i), 0, acq_id, params, nullptr, nullptr, dS + off(i)))) return rc;
+        if (acq_id >= 0) rc = sweep_device(g, dXc + off(i) * d, cnt(i), 0, acq_id, params, nullptr, nullptr, dA + off(i));
+        else rc = sweep_device(g, dXc + off(i) * d, cnt(i), 0, -1, nullptr, dA + off(i), dB + off(i), nullptr);
+        if (rc) return rc;
         CU(cudaEventRecord(c->ev_pc[i & 1], st));
         if (i + 1 < np) {
             CU(cudaMemcpyAsync(dXc + off(i + 1) * d, Xc + off(i + 1) * d, sizeof(double) * cnt(i + 1) * d, cudaMemcpyHostToDevice, sc));
@@ -1195,6 +1203,20 @@ extern "C" int32_t abo_acq_eval(abo_gp* g, int32_t acq_id, const double* params,
     CU(cudaStreamSynchronize(st));
     if (k > 0) topk_finish(heap, hs, 0, top_idx, top_val);
     return ABO_OK;
+}
+
+extern "C" int32_t abo_acq_eval(abo_gp* g, int32_t acq_id, const double* params, const double* Xc, int64_t m,
+                                double* scores, int64_t k, int64_t* top_idx, double* top_val) {
+    int rc = acq_check(g, acq_id, params, Xc, m, k, top_idx, top_val);
+    if (rc) return rc;
+    if (m == 0) return ABO_OK;
+    abo_ctx* c = g->ctx;
+    CU(cudaSetDevice(c->device));
+    if (m > host_piece() && !c->profile) return sweep_host_pieces(g, Xc, m, acq_id, params, nullptr, nullptr, scores, k, top_idx, top_val);
+    double* dXc;
+    if ((rc = ws_get(c, WS_CAND, sizeof(double) * (size_t)m * g->d, (void**)&dXc))) return rc;
+    CU(cudaMemcpyAsync(dXc, Xc, sizeof(double) * m * g->d, cudaMemcpyHostToDevice, c->stream));
+    return acq_eval_common(g, acq_id, params, dXc, m, nullptr, scores, k, top_idx, top_val);
 }
 
 extern "C" int32_t abo_acq_eval_dev(abo_gp* g, int32_t acq_id, const double* params, const double* d_Xc, int64_t m,
