@@ -634,7 +634,6 @@ int gp_unshare(abo_gp* g) {
     CU(cudaMemcpyAsync(g->dMeanC, old.dMeanC, sizeof(double) * old.p, cudaMemcpyDeviceToDevice, st));
     CU(cudaStreamSynchronize(st));
     --*old.share;                                       // > 0 by construction: the other holders keep the set
-    old.hX.clear(); old.hY.clear();
     g->fitted = fitted;
     return ABO_OK;
 }
@@ -692,8 +691,6 @@ extern "C" int32_t abo_gp_fit(abo_gp* g, const double* X, const double* y, int64
     g->fitted = false;
     if (Npad != g->cap_pad || ldx > g->ldx || gp_shared(g)) { int rc = gp_alloc(g, Npad, ldx); if (rc) return rc; }
     g->n = n; g->N = N; g->Npad = Npad;
-    g->hX.assign(X, X + n * g->d);
-    g->hY.assign(y, y + N);
 
     // stage X, y
     double *dXraw, *dYraw;

@@ -185,16 +185,6 @@ static int append_block(abo_gp* g, const double* x, const double* y, int64_t* in
     KL(c);
     CU(cudaStreamSynchronize(st));
     g->n += 1; g->N += p;
-    g->hX.insert(g->hX.end(), x, x + d);
-    {   // host copy of y is out-major [output][point]: re-interleave with the new point
-        const int64_t n_old = g->n - 1;
-        std::vector<double> ny((size_t)g->N);
-        for (int a = 0; a < p; ++a) {
-            for (int64_t i = 0; i < n_old; ++i) ny[(size_t)a * g->n + i] = g->hY[(size_t)a * n_old + i];
-            ny[(size_t)a * g->n + n_old] = y[a];
-        }
-        g->hY.swap(ny);
-    }
     return ABO_OK;
 }
 
@@ -254,8 +244,6 @@ extern "C" int32_t abo_gp_append(abo_gp* g, const double* x, const double* y, in
     KL(c);
     CU(cudaStreamSynchronize(st));
     g->n = n + 1; g->N = n + 1;
-    g->hX.insert(g->hX.end(), x, x + g->d);
-    g->hY.push_back(y[0]);
     return ABO_OK;
 }
 

@@ -72,7 +72,6 @@ struct abo_gp {
     double *dXsT = nullptr, *dL = nullptr, *dLinv = nullptr, *dAlpha = nullptr, *dBeta = nullptr,
            *dDelta = nullptr, *dMeanC = nullptr;
     int* share = nullptr;                 // reference count of the device buffers (clones share them until one writes)
-    std::vector<double> hX, hY;           // host copies of the conditioning data (ABI layout)
 };
 
 // Julia `isless` order on Float64 as an unsigned key: NaN largest, -0.0 < 0.0

@@ -128,7 +128,6 @@ extern "C" int32_t abo_gp_sync(abo_gp* g, int32_t root) {
         g->fitted = false;
         if (cap != g->cap_pad || ldx != g->ldx || gp_shared(g)) { if ((rc = gp_alloc(g, cap, ldx))) return rc; }
         g->n = (int64_t)h[0]; g->N = (int64_t)h[1]; g->Npad = (int64_t)h[2];
-        g->hX.clear(); g->hY.clear();
     }
     const size_t mat = (size_t)g->cap_pad * g->cap_pad;
     NC(nccl().groupStart());

@@ -40,9 +40,21 @@ gp0 = abo.StandardGP(abo.SqExponentialKernel(), c5["noise"], ctx=ctx)
 v_s, g_s, i_s = abo.sharded_nlml_batch(gp0, c5["theta"], c5["X"], c5["y"])
 v_1, g_1, i_1 = abo.nlml_batch(gp0, c5["theta"], c5["X"], c5["y"])
 assert np.array_equal(v_s, v_1) and np.array_equal(g_s, g_1) and np.array_equal(i_s, i_1), "sharded NLML differs"
+# GradientGP: broadcast, then every rank appends the same new point (block append on the received posterior)
+c3 = orc.make_config("C3", n=40, m=300, d=4)
+kg = c3["scale"] * abo.with_lengthscale(abo.ApproxMatern52Kernel(), 1.0 / c3["inv_ls"])
+gm = abo.GradientGP(kg, 5, c3["noise"], ctx=ctx)
+gm = abo.update(gm, c3["X"][:39], c3["Y"][:39]) if rank == 0 else abo.empty_posterior_like(gm, 4)
+abo.sync_posterior(gm, 0)
+gm.gpx.append(c3["X"][39], c3["Y"][39])
+mu_g = abo.posterior_grad_mean(gm, c3["Xc"][:100])
+tg = torch.from_numpy(mu_g).cuda(); rg = tg.clone(); dist.broadcast(rg, 0)
+assert torch.equal(tg, rg), "GradientGP posterior differs between ranks after sync + block append"
+full = abo.update(abo.GradientGP(kg, 5, c3["noise"], ctx=ctx), c3["X"], c3["Y"])
+assert np.max(np.abs(mu_g - abo.posterior_grad_mean(full, c3["Xc"][:100]))) < 1e-9
 if rank == 0:
     s_all, ti_all, tv_all = acq.topk(model, c["Xc"], 100)
     assert list(ti_all) == list(gi), "sharded top-k differs from the single-GPU top-k"
     N = 1536
-    print(f"nccl_check ok: world={world} sync of {2 * N * N * 8 / 1e6:.1f} MB in {dt * 1e3:.2f} ms; top-k and sharded NLML identical", flush=True)
+    print(f"nccl_check ok: world={world} sync of {2 * N * N * 8 / 1e6:.1f} MB in {dt * 1e3:.2f} ms; top-k, sharded NLML and GradientGP sync+append identical", flush=True)
 dist.destroy_process_group()
