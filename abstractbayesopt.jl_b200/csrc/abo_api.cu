@@ -85,8 +85,6 @@ extern "C" int32_t abo_ctx_create(int32_t device, abo_ctx** out) {
     CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
     for (int q = 0; q < 2; ++q) {
-        CU(cudaEventCreateWithFlags(&c->ev_ks[q], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&c->ev_sw[q], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_h2d[q], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_pc[q], cudaEventDisableTiming));
     }
@@ -107,7 +105,7 @@ extern "C" int32_t abo_ctx_destroy(abo_ctx* c) {
     abo_nccl_teardown(c);
     cudaEventDestroy(c->ev_a);
     cudaEventDestroy(c->ev_b);
-    for (int q = 0; q < 2; ++q) { cudaEventDestroy(c->ev_ks[q]); cudaEventDestroy(c->ev_sw[q]); cudaEventDestroy(c->ev_h2d[q]); cudaEventDestroy(c->ev_pc[q]); }
+    for (int q = 0; q < 2; ++q) { cudaEventDestroy(c->ev_h2d[q]); cudaEventDestroy(c->ev_pc[q]); }
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream3);
@@ -829,87 +827,40 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
     mc = std::min<int64_t>(mc, (m + NB - 1) / NB * NB);
     const int64_t vpts = (Npad + g->p - 1) / g->p;                 // virtual points incl. padding columns
     const int npb = (int)((vpts + 127) / 128);
-    // Optional (ABO_SWEEP_OVERLAP=1): the K* tile builder of chunk i+1 on the second stream while the
-    // DMMA contraction of chunk i runs, two K* / mean-partial buffers ping-ponging.  Measured on B200:
-    // 514.5k vs 513.9k candidates/s — no gain, DMMA and DFMA share the FP64 datapath — so it is off by
-    // default (it doubles the K* workspace).
-    const int64_t nchunks = (m + mc - 1) / mc;
-    static const bool want_overlap = getenv("ABO_SWEEP_OVERLAP") != nullptr;
-    const bool overlap = !c->profile && nchunks > 1 && want_overlap;
-    const int nbuf = overlap ? 2 : 1;
-    double *KsAll, *pmeanAll, *sumsq;
+    // (Building the K* tile of chunk i+1 on a second stream while chunk i is contracted was measured: 514.5k vs
+    //  513.9k candidates/s — DMMA and DFMA share the FP64 datapath, there is nothing to overlap — and removed.)
+    double *Ks, *pmean, *sumsq;
     int rc;
-    if ((rc = ws_get(c, WS_KS, sizeof(double) * (size_t)mc * Npad * nbuf, (void**)&KsAll))) return rc;
-    if ((rc = ws_get(c, WS_PMEAN, sizeof(double) * (size_t)npb * mc * nbuf, (void**)&pmeanAll))) return rc;
+    if ((rc = ws_get(c, WS_KS, sizeof(double) * (size_t)mc * Npad, (void**)&Ks))) return rc;
+    if ((rc = ws_get(c, WS_PMEAN, sizeof(double) * (size_t)npb * mc, (void**)&pmean))) return rc;
     if ((rc = ws_get(c, WS_SUMSQ, sizeof(double) * (size_t)T * mc, (void**)&sumsq))) return rc;
-    double* KsB[2] = {KsAll, KsAll + (size_t)mc * Npad * (nbuf - 1)};
-    double* pmB[2] = {pmeanAll, pmeanAll + (size_t)npb * mc * (nbuf - 1)};
-    CUtensorMap tmA, tmB[2];
+    CUtensorMap tmA, tmB;
     if ((rc = make_tmap_k4(&tmA, g->dLinv, Npad, Npad, g->ld))) return rc;
-    for (int q = 0; q < nbuf; ++q)
-        if ((rc = make_tmap_k4(&tmB[q], KsB[q], Npad, mc, Npad))) return rc;
+    if ((rc = make_tmap_k4(&tmB, Ks, Npad, mc, Npad))) return rc;
     AcqSpec a;
     a.acq = acq;
     a.p0 = params ? params[0] : 0.0;
     a.p1 = (params && acq != ACQ_UCB && acq >= 0) ? params[1] : 0.0;
     a.mean_c = g->mean_c[bo];
     a.kss = (bo == 0) ? g->scale : -2.0 * g->s * g->s * g->scale * phi_prime0(g->kind);
-    const int d = g->d;
-    auto build_ks = [&](int64_t c0, int buf, cudaStream_t s_) -> int {
+    for (int64_t c0 = 0; c0 < m; c0 += mc) {
         const int64_t mvalid = std::min(mc, m - c0);
         const int64_t mc_eff = (mvalid + NB - 1) / NB * NB;
-        double* Ks = KsB[buf];
-        double* pmean = pmB[buf];
-        if (d <= 4) launch_ks<4>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
-        else if (d <= 8) launch_ks<8>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
-        else if (d <= 12) launch_ks<12>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
-        else if (d <= 16) launch_ks<16>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
-        else if (d <= 20) launch_ks<20>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
-        else if (d <= 24) launch_ks<24>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
-        else if (d <= 32) launch_ks<32>(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, s_);
-        else
-            ks_build_generic_kernel<<<dim3(npb, (unsigned)(mc_eff / KS_CB)), 128, 0, s_>>>(
-                gp_spec(g), g->dXsT, g->ldx, g->n, g->N, Npad, g->dAlpha, dXc, c0, m, bo, Ks, pmean, mc);
-        KL(c);
-        return ABO_OK;
-    };
-    cudaStream_t st2 = c->stream2;
-    if (overlap) {
-        CU(cudaEventRecord(c->ev_a, st));                 // the builder stream must see the candidates / posterior
-        CU(cudaStreamWaitEvent(st2, c->ev_a, 0));
-        if ((rc = build_ks(0, 0, st2))) return rc;
-        CU(cudaEventRecord(c->ev_ks[0], st2));
-    }
-    int64_t ci = 0;
-    for (int64_t c0 = 0; c0 < m; c0 += mc, ++ci) {
-        const int64_t mvalid = std::min(mc, m - c0);
-        const int64_t mc_eff = (mvalid + NB - 1) / NB * NB;
-        const int buf = overlap ? (int)(ci & 1) : 0;
-        if (overlap) {
-            CU(cudaStreamWaitEvent(st, c->ev_ks[buf], 0));
-            if (c0 + mc < m) {                            // next chunk's K* into the other buffer
-                if (ci >= 1) CU(cudaStreamWaitEvent(st2, c->ev_sw[buf ^ 1], 0));   // its last reader is done
-                if ((rc = build_ks(c0 + mc, buf ^ 1, st2))) return rc;
-                CU(cudaEventRecord(c->ev_ks[buf ^ 1], st2));
-            }
-        } else {
-            if ((rc = prof_mark(c))) return rc;
-            if ((rc = build_ks(c0, 0, st))) return rc;
-            if ((rc = prof_mark(c))) return rc;
-        }
+        if ((rc = prof_mark(c))) return rc;
+        if ((rc = launch_ks_d(c, g, dXc, c0, m, bo, Ks, pmean, mc_eff, mc, npb, st))) return rc;
+        if ((rc = prof_mark(c))) return rc;
         if ((rc = prof_mark(c))) return rc;
         SweepParams sp;
         sp.T = T; sp.ncb = (int)(mc_eff / NB); sp.sumsq = sumsq; sp.sumsq_ld = mc;
-        sweep_tma_kernel<<<std::min(c->sms, sp.T * sp.ncb), SW_THREADS, SW_SMEM_BYTES, st>>>(tmA, tmB[buf], sp);
+        sweep_tma_kernel<<<std::min(c->sms, sp.T * sp.ncb), SW_THREADS, SW_SMEM_BYTES, st>>>(tmA, tmB, sp);
         KL(c);
         if ((rc = prof_mark(c))) return rc;
         if ((rc = prof_mark(c))) return rc;
         acq_epilogue_kernel<<<(unsigned)((mvalid + 255) / 256), 256, 0, st>>>(
-            a, pmB[buf], npb, sumsq, T, mc, mvalid, d_mean ? d_mean + c0 : nullptr, d_var ? d_var + c0 : nullptr,
+            a, pmean, npb, sumsq, T, mc, mvalid, d_mean ? d_mean + c0 : nullptr, d_var ? d_var + c0 : nullptr,
             d_score ? d_score + c0 : nullptr);
         KL(c);
         if ((rc = prof_mark(c))) return rc;
-        if (overlap) CU(cudaEventRecord(c->ev_sw[buf], st));
         if (c->profile && c->prof_used >= 6 * 512) {       // bound the event pool
             CU(cudaStreamSynchronize(st));
             if ((rc = prof_collect(c))) return rc;
@@ -987,13 +938,7 @@ extern "C" int32_t abo_acq_eval_grad(abo_gp* g, int32_t acq_id, const double* pa
     for (int64_t c0 = 0; c0 < m; c0 += mc) {
         const int64_t mvalid = std::min(mc, m - c0);
         const int64_t mpad = (mvalid + NB - 1) / NB * NB;
-        if (d <= 4) launch_ks<4>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
-        else if (d <= 8) launch_ks<8>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
-        else if (d <= 12) launch_ks<12>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
-        else if (d <= 16) launch_ks<16>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
-        else if (d <= 20) launch_ks<20>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
-        else if (d <= 24) launch_ks<24>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
-        else launch_ks<32>(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st);
+        if ((rc = launch_ks_d(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st))) return rc;
         KL(c);
         GemmParams w{};                                        // W = L^-1 K*^T   (k <= row)
         w.A = g->dLinv; w.lda = g->ld; w.B = Ks; w.ldb = Npad; w.C = W; w.ldc = mpad;
@@ -1050,15 +995,7 @@ extern "C" int32_t abo_gp_posterior_cov(abo_gp* g, const double* Xc, int64_t m, 
     for (int bo = 0; bo < outputs; ++bo) {
         double* Kb = Ks + (size_t)bo * mp * Npad;
         double* pm = pmean + (size_t)bo * mp;                      // (unused partial means)
-        if (d <= 4) launch_ks<4>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
-        else if (d <= 8) launch_ks<8>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
-        else if (d <= 12) launch_ks<12>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
-        else if (d <= 16) launch_ks<16>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
-        else if (d <= 20) launch_ks<20>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
-        else if (d <= 24) launch_ks<24>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
-        else if (d <= 32) launch_ks<32>(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st);
-        else return abo_fail(ABO_ERR_INVALID, "posterior covariance supports d <= 32");
-        KL(c);
+        if ((rc = launch_ks_d(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st))) return rc;
     }
     GemmParams w{};                                                // W = L^-1 K*^T
     w.A = g->dLinv; w.lda = g->ld; w.B = Ks; w.ldb = Npad; w.C = W; w.ldc = Mpad;

@@ -41,7 +41,6 @@ struct abo_ctx {
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
     cudaEvent_t ev_p[3] = {nullptr, nullptr, nullptr};            // panel-chain split of the Cholesky
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
-    cudaEvent_t ev_ks[2] = {nullptr, nullptr}, ev_sw[2] = {nullptr, nullptr};   // K* builder / contraction ping-pong
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_pc[2] = {nullptr, nullptr};  // candidate pieces: staged / evaluated
     WsBuf ws[WS_COUNT];
     void* pinned = nullptr;

@@ -24,7 +24,7 @@ typedef int (*Broadcast_t)(const void*, void*, size_t, int, int, void*, cudaStre
 typedef int (*AllGather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*Group_t)(void);
 typedef const char* (*ErrStr_t)(int);
-constexpr int NCCL_UINT8 = 1, NCCL_FLOAT64 = 8;
+constexpr int NCCL_FLOAT64 = 8;
 
 struct Nccl {
     bool ok = false;
