@@ -7,6 +7,7 @@
 module AboCuda
 
 using LinearAlgebra
+import AbstractGPs, ForwardDiff
 using ..AbstractBayesOpt: AbstractSurrogate, AbstractAcquisition, ExpectedImprovement,
     ProbabilityImprovement, UpperConfidenceBound, StandardGP, extract_scale_and_lengthscale
 import ..AbstractBayesOpt: update, posterior_mean, posterior_var, nlml, nlml_ls, prep_input, prep_output,
@@ -49,7 +50,10 @@ is a device handle instead of an AbstractGPs.PosteriorGP."""
 struct CuStandardGP{T} <: AbstractSurrogate
     prior::StandardGP{T}              # keeps kernel / noise / mean exactly as the reference stores them
     gpx::Union{Nothing,Handle}
+    X::Union{Nothing,Matrix{Float64}} # conditioning data (d x n) the handle holds: enables the O(n^2) append
+    y::Union{Nothing,Vector{Float64}}
 end
+CuStandardGP(prior::StandardGP, gpx) = CuStandardGP(prior, gpx, nothing, nothing)
 CuStandardGP(kernel, noise_var; mean=nothing) = CuStandardGP(StandardGP(kernel, noise_var; mean=mean), nothing)
 
 get_lengthscale(m::CuStandardGP) = get_lengthscale(m.prior)
@@ -71,7 +75,7 @@ function Base.copy(m::CuStandardGP)                                           # 
     m.gpx === nothing && return CuStandardGP(m.prior, nothing)
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:abo_gp_clone, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), m.gpx.h, r))
-    CuStandardGP(m.prior, Handle(r[]))
+    CuStandardGP(m.prior, Handle(r[]), m.X, m.y)      # O(1): the clone shares the device buffers (copy-on-write)
 end
 
 points(xs::Vector{<:AbstractVector}) = reduce(hcat, xs)                       # d x n column-major = point-major
@@ -81,6 +85,17 @@ function update(m::CuStandardGP, xs::Vector, ys::Vector)                      # 
     X = Matrix{Float64}(points(xs)); d, n = size(X)
     length(ys) == n || throw(DimensionMismatch("xs and ys have different lengths"))
     y = collect(Float64, ys)
+    # one more observation on top of what the handle already holds (the BO loop, bayesian_opt.jl:120-125):
+    # O(n^2) row append on a copy-on-write clone instead of the O(n^3) re-fit
+    if m.gpx !== nothing && m.X !== nothing && size(m.X, 2) == n - 1 && size(m.X, 1) == d &&
+       view(X, :, 1:n-1) == m.X && view(y, 1:n-1) == m.y
+        c = copy(m); info = Ref{Int64}(0)
+        xn = X[:, n]; yn = [y[n]]
+        rc = GC.@preserve xn yn ccall((:abo_gp_append, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}),
+            c.gpx.h, xn, yn, info)
+        check(rc, info[])
+        return CuStandardGP(m.prior, c.gpx, X, y)
+    end
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:abo_gp_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}),
         ctx().h, kernel_id(m), d, 1, r))
@@ -92,7 +107,7 @@ function update(m::CuStandardGP, xs::Vector, ys::Vector)                      # 
     rc = GC.@preserve X y ccall((:abo_gp_fit, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ref{Int64}),
         h.h, X, y, n, info)
     check(rc, info[])
-    CuStandardGP(m.prior, h)
+    CuStandardGP(m.prior, h, X, y)
 end
 
 function posterior(m::CuStandardGP, x::AbstractVector, want_mean::Bool, want_var::Bool)
@@ -126,6 +141,17 @@ end
 (a::ExpectedImprovement)(m::CuStandardGP, x::AbstractVector) = acq_eval(a, m, x)[1]
 (a::ProbabilityImprovement)(m::CuStandardGP, x::AbstractVector) = acq_eval(a, m, x)[1]
 (a::UpperConfidenceBound)(m::CuStandardGP, x::AbstractVector) = acq_eval(a, m, x)[1]
+
+# acquisition value and its analytic gradient for a batch of points in one call: what a batched replacement of
+# the finite-difference refinement loop (acq_utils.jl:55-71) evaluates per step
+function acq_value_grad(a::AbstractAcquisition, m::CuStandardGP, x::AbstractVector)
+    Xc = Matrix{Float64}(points(collect(x))); d, mcount = size(Xc)
+    scores = Vector{Float64}(undef, mcount); grad = Matrix{Float64}(undef, d, mcount); p = acq_params(a)
+    check(GC.@preserve Xc scores grad p ccall((:abo_acq_eval_grad, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        m.gpx.h, acq_id(a), p, Xc, mcount, scores, grad, C_NULL, C_NULL))
+    scores, grad                                                   # grad[:, c] = d acq / d x_c
+end
 
 # ---- nlml with ForwardDiff.Dual parameters (bayesian_opt.jl:284): value + analytic gradient from the
 #      device, re-assembled into a Dual (SURVEY H7)
