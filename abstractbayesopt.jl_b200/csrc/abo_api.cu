@@ -49,6 +49,8 @@ static int configure_kernels() {
     CU(configure_gemm<MC, MC, EPI_STORE>());
     CU(cudaFuncSetAttribute(gemm_small_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<32, 8>::SMEM_BYTES));
     CU(cudaFuncSetAttribute(gemm_small_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmS<64, 8>::SMEM_BYTES));
+    CU(cudaFuncSetAttribute(gemm_k128_kernel<16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmK128<16, 128>::SMEM_BYTES));
+    CU(cudaFuncSetAttribute(gemm_k128_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmK128<32, 32>::SMEM_BYTES));
     CU(cudaFuncSetAttribute(fill_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 96 * 8));
     CU(cudaFuncSetAttribute(potf2_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_BYTES));
     CU(cudaFuncSetAttribute(sweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
@@ -322,6 +324,7 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
     bool s3_pending = false;
     cudaStream_t s3 = c->stream3;
     static const bool split = getenv("ABO_POTRF_NOSPLIT") == nullptr;
+    static const bool k128 = getenv("ABO_POTRF_NOK128") == nullptr;
     static const bool trace = getenv("ABO_POTRF_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;           // per outer block: start, panel done, U_next done (sp), U_rest start, done (su)
     auto mark = [&](cudaStream_t s_) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); tev.push_back(e); } };
@@ -370,9 +373,14 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
                 // (the three critical kernels stay back to back on the panel stream so that PDL applies;
                 //  the bulk stream picks up after them — it has a full potf2 of slack)
                 GemmParams g1 = g; g1.M = NB;                              // tile row jp+1
-                if ((rc2 = gemm_panel(g1, sp, pdl))) return rc2;
                 GemmParams s1 = s; s1.M = NB; s1.N = NB; s1.flags = 0;     // diagonal tile (jp+1, jp+1)
-                if ((rc2 = gemm_panel(s1, sp, pdl))) return rc2;
+                if (k128) {                                                // latency kernels: 8 / 16 CTAs, one load group
+                    CU(launch_pdl(gemm_k128_kernel<16, 128>, dim3(1, 8, 1), dim3(128), GemmK128<16, 128>::SMEM_BYTES, sp, pdl, g1)); KL(c);   // in place: whole rows per CTA
+                    CU(launch_pdl(gemm_k128_kernel<32, 32>, dim3(4, 4, 1), dim3(128), GemmK128<32, 32>::SMEM_BYTES, sp, pdl, s1)); KL(c);
+                } else {
+                    if ((rc2 = gemm_panel(g1, sp, pdl))) return rc2;
+                    if ((rc2 = gemm_panel(s1, sp, pdl))) return rc2;
+                }
                 CU(cudaEventRecord(c->ev_p[1], sp));                       // potf2(jp), L[jp+1, jp] final
                 CU(cudaStreamWaitEvent(s3, c->ev_p[1], 0));
                 GemmParams g2 = g; g2.A = P + (int64_t)NB * ld; g2.C = P + (int64_t)NB * ld; g2.M = rem - NB;

@@ -287,6 +287,71 @@ inline cudaError_t launch_gemm_small(const GemmParams& p, int batch, cudaStream_
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// Latency kernels for the two GEMMs on the critical chain of the Cholesky (next diagonal tile: TRSM-as-GEMM and
+// its SYRK, M = N = K = 128): small TM x TN output tiles -> 8 / 16 CTAs of 4 warps, the whole k-range staged by
+// ONE cp.async group, no pipeline to fill or drain.  K-contiguous operands, store epilogue.
+//   <16, 128>: a CTA owns whole rows, so C may alias A (the in-place TRSM)      <32, 32>: the SYRK of the tile
+// ------------------------------------------------------------------------------------------
+template <int TM, int TN>
+struct GemmK128 {
+    static constexpr int WM = TM / 16, WN = 4 / WM, WNC = TN / WN, NT = WNC / 8;
+    static constexpr int SMEM_BYTES = 32 * (TM + TN) * 4 * (int)sizeof(double);
+};
+template <int TM, int TN>
+__global__ void __launch_bounds__(128) gemm_k128_kernel(GemmParams p) {
+    using S = GemmK128<TM, TN>;
+    extern __shared__ __align__(16) double smem[];
+    double* sA = smem;
+    double* sB = smem + 32 * TM * 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    pdl_launch_dependents();
+    pdl_wait();
+#pragma unroll
+    for (int q = 0; q < TM * 64 / 128; ++q) {          // TM rows x 64 chunks of 16 B
+        const int c = tid + 128 * q, row = c >> 6, ch = c & 63;
+        cp_async16(sA + ((((ch >> 1) * TM + row) << 2) + ((ch & 1) << 1)), p.A + (int64_t)(m0 + row) * p.lda + 2 * ch);
+    }
+#pragma unroll 8
+    for (int q = 0; q < TN * 64 / 128; ++q) {
+        const int c = tid + 128 * q, row = c >> 6, ch = c & 63;
+        cp_async16(sB + ((((ch >> 1) * TN + row) << 2) + ((ch & 1) << 1)), p.B + (int64_t)(n0 + row) * p.ldb + 2 * ch);
+    }
+    cp_async_commit();
+    const int wm = (warp % S::WM) * 16, wn = (warp / S::WM) * S::WNC;
+    double acc[2][S::NT][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < S::NT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll 4
+    for (int kk = 0; kk < 32; ++kk) {
+        double a[2], b[S::NT];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a[i] = sA[((kk * TM + wm + i * 8 + (lane >> 2)) << 2) + (lane & 3)];
+#pragma unroll
+        for (int j = 0; j < S::NT; ++j) b[j] = sB[((kk * TN + wn + j * 8 + (lane >> 2)) << 2) + (lane & 3)];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < S::NT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < S::NT; ++j) {
+            double2* dst = reinterpret_cast<double2*>(p.C + (int64_t)(m0 + wm + i * 8 + (lane >> 2)) * p.ldc + n0 + wn + j * 8 + 2 * (lane & 3));
+            double2 v;
+            v.x = p.alpha * acc[i][j][0];
+            v.y = p.alpha * acc[i][j][1];
+            if (p.beta != 0.0) { const double2 o = *dst; v.x += p.beta * o.x; v.y += p.beta * o.y; }
+            *dst = v;
+        }
+}
+
 template <int LA, int LB, int EPI>
 inline cudaError_t configure_gemm() {   // per device: opt in to > 48 KB dynamic shared memory
     return cudaFuncSetAttribute(gemm_dmma_kernel<LA, LB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
