@@ -322,6 +322,7 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
     CU(cudaStreamWaitEvent(su, c->ev_a, 0));
     bool rest_pending = false;
     bool s3_pending = false;
+    bool boundary_split = false;
     cudaStream_t s3 = c->stream3;
     static const bool split = getenv("ABO_POTRF_NOSPLIT") == nullptr;
     static const bool k128 = getenv("ABO_POTRF_NOK128") == nullptr;
@@ -364,7 +365,19 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
             s.C = Ajj + (int64_t)NB * (ld + 1); s.ldc = ld;
             s.M = rem; s.N = ncol; s.K = NB; s.alpha = -1.0; s.beta = 1.0; s.flags = LOWER_ONLY;
             int rc2;
-            if (!split || ncol <= 0 || rem <= NB) {
+            if (split && k128 && ncol <= 0 && rem > NB) {
+                // last panel of the outer block: the next potf2 waits for tile row je of this TRSM and for the
+                // update of tile (je, je) only (diag_next below); the other rows go to the bulk stream
+                GemmParams g1 = g; g1.M = NB;
+                CU(launch_pdl(gemm_k128_kernel<16, 128>, dim3(1, 8, 1), dim3(128), GemmK128<16, 128>::SMEM_BYTES, sp, pdl, g1)); KL(c);
+                CU(cudaEventRecord(c->ev_p[1], sp));
+                CU(cudaStreamWaitEvent(s3, c->ev_p[1], 0));
+                GemmParams g2 = g; g2.A = P + (int64_t)NB * ld; g2.C = P + (int64_t)NB * ld; g2.M = rem - NB;
+                if ((rc2 = gemm_panel(g2, s3, false))) return rc2;
+                CU(cudaEventRecord(c->ev_p[2], s3));
+                s3_pending = true;
+                boundary_split = true;
+            } else if (!split || ncol <= 0 || rem <= NB) {
                 if ((rc2 = gemm_panel(g, sp, pdl))) return rc2;
                 if ((rc2 = gemm_panel(s, sp, pdl))) return rc2;
             } else {
@@ -396,16 +409,17 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
                 // panel stream wait for the bulk right after that potf2 has been enqueued (below)
             }
         }
-        if (s3_pending) { CU(cudaStreamWaitEvent(sp, c->ev_p[2], 0)); s3_pending = false; }
+        if (s3_pending && !boundary_split) { CU(cudaStreamWaitEvent(sp, c->ev_p[2], 0)); s3_pending = false; }
         mark(sp);
         if (je >= T) break;
         SyrkParams u;
-        u.C = A; u.ld = ld; u.kcol0 = Jb * NB; u.nk = (je - Jb) * (NB / 16);
+        u.C = A; u.ld = ld; u.kcol0 = Jb * NB; u.nk = (je - Jb) * (NB / 16); u.skip_first = 0;
         // ---- U_rest(b) on the second stream: needs panel(b) (event) and, by stream order, U_rest(b-1)
         const int jn = std::min(je + (ramp ? std::min(step + 2, OB) : OB), T);
         CU(cudaEventRecord(c->ev_a, sp));
         if (jn < T) {
             CU(cudaStreamWaitEvent(su, c->ev_a, 0));
+            if (boundary_split) CU(cudaStreamWaitEvent(su, c->ev_p[2], 0));   // the bulk rows of the last TRSM
             u.row_t0 = jn; u.col_t0 = jn;
             mark(su);
             syrk_tma_kernel<<<dim3(T - jn, T - jn), SW_THREADS, SY_SMEM_BYTES, su>>>(tmL, u);
@@ -415,6 +429,20 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
         // ---- U_next(b) on the panel stream: the next block's columns; they were last touched by
         //      U_rest(b-1), so wait for it
         if (rest_pending) CU(cudaStreamWaitEvent(sp, c->ev_b, 0));
+        cudaStream_t sn = sp;                              // stream of the (bulk of the) U_next update
+        bool pdl_next = pdl && !rest_pending;
+        if (boundary_split) {
+            // critical chain: only tile (je, je) — K = width of the outer block — then straight on to potf2(je);
+            // the rest of U_next follows the bulk TRSM on the third stream (it has that potf2 of slack)
+            GemmParams dn{};
+            dn.A = A + (int64_t)je * NB * ld + (int64_t)Jb * NB; dn.lda = ld;
+            dn.B = dn.A; dn.ldb = ld;
+            dn.C = A + (int64_t)je * NB * (ld + 1); dn.ldc = ld;
+            dn.M = NB; dn.N = NB; dn.K = (je - Jb) * NB; dn.alpha = -1.0; dn.beta = 1.0; dn.flags = 0;
+            CU(launch_pdl(gemm_k128_kernel<32, 32>, dim3(4, 4, 1), dim3(128), GemmK128<32, 32>::SMEM_BYTES, sp, pdl_next, dn)); KL(c);
+            if (rest_pending) CU(cudaStreamWaitEvent(s3, c->ev_b, 0));
+            sn = s3; pdl_next = false; u.skip_first = 1;
+        }
         if ((T - je) * (jn - je) <= small_next) {
             // few tiles: one 128x128xK tile per CTA would leave most SMs idle for a full tile time
             // (~55 us); 32-row tiles finish the slab in ~1/3 of that
@@ -423,14 +451,19 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
             nx.B = nx.A; nx.ldb = ld;
             nx.C = A + (int64_t)je * NB * (ld + 1); nx.ldc = ld;
             nx.M = (T - je) * NB; nx.N = (jn - je) * NB; nx.K = (je - Jb) * NB;
-            nx.alpha = -1.0; nx.beta = 1.0; nx.flags = LOWER_ONLY;
-            CU(launch_pdl(gemm_small_kernel<32, 8>, dim3(nx.N / BN, nx.M / 32, 1), dim3(256), GemmS<32, 8>::SMEM_BYTES, sp,
-                          pdl && !rest_pending, nx));
+            nx.alpha = -1.0; nx.beta = 1.0; nx.flags = LOWER_ONLY | (boundary_split ? SKIP_FIRST : 0);
+            CU(launch_pdl(gemm_small_kernel<32, 8>, dim3(nx.N / BN, nx.M / 32, 1), dim3(256), GemmS<32, 8>::SMEM_BYTES, sn,
+                          pdl_next, nx));
         } else {
             u.row_t0 = je; u.col_t0 = je;
-            CU(launch_pdl(syrk_tma_kernel, dim3(jn - je, T - je), dim3(SW_THREADS), SY_SMEM_BYTES, sp, pdl && !rest_pending, tmL, u));
+            CU(launch_pdl(syrk_tma_kernel, dim3(jn - je, T - je), dim3(SW_THREADS), SY_SMEM_BYTES, sn, pdl_next, tmL, u));
         }
         KL(c);
+        if (boundary_split) {                              // the next potf2's TRSM needs it: waited for right after that potf2
+            CU(cudaEventRecord(c->ev_p[2], s3));
+            s3_pending = true;
+            boundary_split = false;
+        }
         mark(sp);
         if (jn < T) { CU(cudaEventRecord(c->ev_b, su)); rest_pending = true; }
     }

@@ -31,7 +31,8 @@ enum GemmFlags {
     KLO_M = 1,        // k starts at the tile's first row      (A^T-type lower operands)
     KLO_N = 2,        // k starts at the tile's first column   (B lower triangular, k >= n)
     KHI_M = 4,        // k stops after the tile's last row     (A lower triangular, k <= m)
-    LOWER_ONLY = 8    // skip tiles strictly above the diagonal
+    LOWER_ONLY = 8,   // skip tiles strictly above the diagonal
+    SKIP_FIRST = 16   // leave out the first 128 x 128 tile of C (updated elsewhere)
 };
 
 struct GemmParams {
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 2) gemm_small_kernel(Ge
     const int m0 = blockIdx.y * BMT, n0 = blockIdx.x * BN;
     pdl_launch_dependents();
     if ((p.flags & LOWER_ONLY) && n0 > m0 + p.lower_shift) return;
+    if ((p.flags & SKIP_FIRST) && m0 < 128 && n0 == 0) return;
     const double* A = p.A + (int64_t)blockIdx.z * p.strideA;
     const double* B = p.B + (int64_t)blockIdx.z * p.strideB;
     const int nk = p.K / BK;
@@ -308,36 +310,39 @@ __global__ void __launch_bounds__(128) gemm_k128_kernel(GemmParams p) {
     const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
     pdl_launch_dependents();
     pdl_wait();
-#pragma unroll
-    for (int q = 0; q < TM * 64 / 128; ++q) {          // TM rows x 64 chunks of 16 B
-        const int c = tid + 128 * q, row = c >> 6, ch = c & 63;
-        cp_async16(sA + ((((ch >> 1) * TM + row) << 2) + ((ch & 1) << 1)), p.A + (int64_t)(m0 + row) * p.lda + 2 * ch);
-    }
-#pragma unroll 8
-    for (int q = 0; q < TN * 64 / 128; ++q) {
-        const int c = tid + 128 * q, row = c >> 6, ch = c & 63;
-        cp_async16(sB + ((((ch >> 1) * TN + row) << 2) + ((ch & 1) << 1)), p.B + (int64_t)(n0 + row) * p.ldb + 2 * ch);
-    }
-    cp_async_commit();
     const int wm = (warp % S::WM) * 16, wn = (warp / S::WM) * S::WNC;
     double acc[2][S::NT][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < S::NT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-    cp_async_wait<0>();
-    __syncthreads();
+    for (int k0 = 0; k0 < p.K; k0 += 128) {            // K = 128 on the inner chain, up to the outer block width at its end
+        if (k0) __syncthreads();
+#pragma unroll
+        for (int q = 0; q < TM * 64 / 128; ++q) {      // TM rows x 64 chunks of 16 B
+            const int c = tid + 128 * q, row = c >> 6, ch = c & 63;
+            cp_async16(sA + ((((ch >> 1) * TM + row) << 2) + ((ch & 1) << 1)), p.A + (int64_t)(m0 + row) * p.lda + k0 + 2 * ch);
+        }
+#pragma unroll 8
+        for (int q = 0; q < TN * 64 / 128; ++q) {
+            const int c = tid + 128 * q, row = c >> 6, ch = c & 63;
+            cp_async16(sB + ((((ch >> 1) * TN + row) << 2) + ((ch & 1) << 1)), p.B + (int64_t)(n0 + row) * p.ldb + k0 + 2 * ch);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
 #pragma unroll 4
-    for (int kk = 0; kk < 32; ++kk) {
-        double a[2], b[S::NT];
+        for (int kk = 0; kk < 32; ++kk) {
+            double a[2], b[S::NT];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) a[i] = sA[((kk * TM + wm + i * 8 + (lane >> 2)) << 2) + (lane & 3)];
+            for (int i = 0; i < 2; ++i) a[i] = sA[((kk * TM + wm + i * 8 + (lane >> 2)) << 2) + (lane & 3)];
 #pragma unroll
-        for (int j = 0; j < S::NT; ++j) b[j] = sB[((kk * TN + wn + j * 8 + (lane >> 2)) << 2) + (lane & 3)];
+            for (int j = 0; j < S::NT; ++j) b[j] = sB[((kk * TN + wn + j * 8 + (lane >> 2)) << 2) + (lane & 3)];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < S::NT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < S::NT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i)

@@ -202,6 +202,7 @@ struct SyrkParams {
     int row_t0, col_t0; // first row tile / column tile of this launch's grid
     int kcol0;          // first column of the panel block
     int nk;             // k16 steps (panel width / 16)
+    int skip_first;     // leave out tile (row_t0, col_t0): it was updated by the latency kernel on the critical chain
 };
 
 __global__ void __launch_bounds__(SW_THREADS, 1)
@@ -212,7 +213,7 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmL, SyrkParams p) {
     uint64_t* empty = full + SY_STAGES;
     const int it = p.row_t0 + blockIdx.y, jt = p.col_t0 + blockIdx.x;
     pdl_launch_dependents();
-    if (jt > it) return;
+    if (jt > it || (p.skip_first && blockIdx.x == 0 && blockIdx.y == 0)) return;
     pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = it * 128, n0 = jt * 128;
