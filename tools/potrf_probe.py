@@ -21,6 +21,7 @@ for n in sizes:
     fl = n ** 3 / 3 + n ** 2 / 2
     L = torch.tril(A)
     err = (torch.linalg.norm(L @ L.T - K0) / torch.linalg.norm(K0)).item()
-    ck = ctx.potf2_clocks(); names = ["load", "factor", "storeL", "inv0", "invL", "storeD"]
-    print("   potf2 phases (cycles):", {names[i]: ck[i + 1] - ck[i] for i in range(6)}, "total", ck[6] - ck[0], "| sub-panel 0: diag", ck[8] - ck[1], "trsm", ck[9] - ck[8], "update", ck[10] - ck[9], "| inverse round 3: early-S done -> D_3 ready", ck[12] - ck[11], "X_33", ck[13] - ck[12], "multiply+store", ck[14] - ck[13], "| F done at", ck[2] - ck[0], "I done at", ck[14] - ck[0])
+    ck = ctx.potf2_clocks()        # stamps of CTA 0 of the last potf2 launch: 0 start, 1 staged, 2 factor group done, 6 end, 11-14 last inverse round
+    print("   potf2 (cycles): staged", ck[1] - ck[0], "| factor group done", ck[2] - ck[0], "| inverse round 3: X_33", ck[13] - ck[12],
+          "multiply+store", ck[14] - ck[13], "| kernel end", ck[6] - ck[0])
     print(f"n={n} potrf {best:.3f} ms  {fl / best / 1e9:.2f} TFLOP/s  relres={err:.2e}", flush=True)
