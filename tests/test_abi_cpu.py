@@ -108,3 +108,24 @@ def test_lockstep_lbfgsb_on_analytic_problems(built):
     assert conv[ok].all() and np.max(np.abs(X[ok] - centers[ok])) < 1e-4
     assert abs(X[3, 0] - 2.0) < 1e-12 and abs(X[3, 1]) < 1e-4              # clipped to the upper bound
     assert max(calls) <= R and len(calls) < 200                            # batched: one call per trial step
+
+
+def test_lockstep_lbfgsb_rosenbrock_with_history(built):
+    """Curved valleys need the quasi-Newton history (vectorised two-loop recursion): 40 Rosenbrock problems from
+    random starts, free and with an active upper bound."""
+    import numpy as np
+    abo = built
+
+    def fg(X, idx):
+        x = X[idx]
+        f = (1 - x[:, 0]) ** 2 + 100 * (x[:, 1] - x[:, 0] ** 2) ** 2
+        g = np.stack([-2 * (1 - x[:, 0]) - 400 * x[:, 0] * (x[:, 1] - x[:, 0] ** 2), 200 * (x[:, 1] - x[:, 0] ** 2)], 1)
+        return f, g
+
+    x0 = np.random.default_rng(0).uniform(-2, 2, (40, 2))
+    X, f, conv, failed = abo.lockstep_lbfgsb(fg, x0, np.array([-2.0, -2.0]), np.array([2.0, 2.0]), max_iter=300, g_tol=1e-8,
+                                             f_abstol=0.0)
+    assert conv.all() and not failed.any() and np.max(np.abs(X - 1.0)) < 1e-6
+    X, f, conv, failed = abo.lockstep_lbfgsb(fg, x0, np.array([-2.0, -2.0]), np.array([0.5, 2.0]), max_iter=300, g_tol=1e-8,
+                                             f_abstol=0.0)
+    assert conv.all() and np.max(np.abs(X - np.array([0.5, 0.25]))) < 1e-6 and np.max(np.abs(f - 0.25)) < 1e-10
