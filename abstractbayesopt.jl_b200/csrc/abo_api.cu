@@ -96,10 +96,14 @@ extern "C" int32_t abo_ctx_create(int32_t device, abo_ctx** out) {
     return ABO_OK;
 }
 
+static void gp_free_device(abo_gp* g);
+
 extern "C" int32_t abo_ctx_destroy(abo_ctx* c) {
     if (!c) return ABO_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (abo_gp* g : c->live) { gp_free_device(g); g->ctx = nullptr; }   // orphaned: only abo_gp_destroy is valid on them
+    c->live.clear();
     for (auto& b : c->ws) if (b.ptr) cudaFree(b.ptr);
     gp_pool_clear(c);
     for (auto e : c->prof_events) cudaEventDestroy(e);
@@ -691,13 +695,14 @@ extern "C" int32_t abo_gp_create(abo_ctx* ctx, int32_t kernel_id, int32_t d, int
     g->ctx = ctx; g->kind = kernel_id; g->d = d; g->p = p;
     g->s = 1.0; g->scale = 1.0; g->noise = 0.0;
     g->mean_c.assign(p, 0.0);
+    ctx->live.insert(g);
     *out = g;
     return ABO_OK;
 }
 
 extern "C" int32_t abo_gp_destroy(abo_gp* g) {
     if (!g) return ABO_OK;
-    gp_free_device(g);
+    if (g->ctx) { g->ctx->live.erase(g); gp_free_device(g); }
     delete g;
     return ABO_OK;
 }
@@ -721,6 +726,7 @@ static KSpec gp_spec(const abo_gp* g) {
 extern "C" int32_t abo_gp_fit(abo_gp* g, const double* X, const double* y, int64_t n, int64_t* info_out) {
     if (!g || !X || !y) return abo_fail(ABO_ERR_INVALID, "null argument");
     if (n < 1) return abo_fail(ABO_ERR_DIM, "need at least one observation");
+    if (!g->ctx) return abo_fail(ABO_ERR_INVALID, "the context of this handle has been destroyed");
     abo_ctx* c = g->ctx;
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
@@ -777,6 +783,7 @@ extern "C" int32_t abo_gp_clone(const abo_gp* g, abo_gp** out) {
     abo_gp* n = new (std::nothrow) abo_gp(*g);          // shares the device buffers; a writer un-shares first
     if (!n) return abo_fail(ABO_ERR_ALLOC, "host allocation failed");
     if (n->share) ++*n->share;
+    if (n->ctx) n->ctx->live.insert(n);
     *out = n;
     return ABO_OK;
 }

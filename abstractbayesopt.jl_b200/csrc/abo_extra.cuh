@@ -258,6 +258,7 @@ extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, i
     if (!g || !X || !y || !logparams || !nlml) return abo_fail(ABO_ERR_INVALID, "null argument");
     if (n < 1) return abo_fail(ABO_ERR_DIM, "need at least one observation");
     if (R <= 0) return ABO_OK;
+    if (!g->ctx) return abo_fail(ABO_ERR_INVALID, "the context of this handle has been destroyed");
     abo_ctx* c = g->ctx;
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;

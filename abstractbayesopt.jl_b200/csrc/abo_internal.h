@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cstring>
 #include <utility>
+#include <unordered_set>
 #include <vector>
 #include <cuda_runtime.h>
 
@@ -55,6 +56,9 @@ struct abo_ctx {
     // NCCL (one rank per context)
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    // handles created on this context: abo_ctx_destroy orphans the ones still alive (bindings whose finalizers
+    // run in arbitrary order — Python at interpreter exit, Julia's GC — may destroy the context first)
+    std::unordered_set<abo_gp*> live;
     // released posterior buffer sets kept for re-use (a BO loop allocates and frees one per iteration)
     struct GpBufSet { int64_t cap_pad, ldx; int d, p; double* ptr[7]; };
     std::vector<GpBufSet> gp_pool;

@@ -103,6 +103,7 @@ static int bcast_doubles(abo_ctx* c, std::vector<double>& h, int root) {
 
 extern "C" int32_t abo_gp_sync(abo_gp* g, int32_t root) {
     if (!g) return abo_fail(ABO_ERR_INVALID, "null gp");
+    if (!g->ctx) return abo_fail(ABO_ERR_INVALID, "the context of this handle has been destroyed");
     abo_ctx* c = g->ctx;
     if (c->nranks == 1) return ABO_OK;
     if (!c->nccl_comm) return abo_fail(ABO_ERR_NCCL, "context has no NCCL communicator (abo_ctx_init_rank)");

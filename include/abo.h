@@ -57,6 +57,8 @@ const char* abo_last_error(void);          /* thread-local message of the last f
 
 /* ---- context ------------------------------------------------------------------------- */
 int32_t abo_ctx_create(int32_t device, abo_ctx** out);
+/* Handles of this context that are still alive are orphaned: their device memory is released and only
+ * abo_gp_destroy remains valid on them (finalizers of GC'd bindings run in arbitrary order). */
 int32_t abo_ctx_destroy(abo_ctx* ctx);
 int32_t abo_ctx_device(const abo_ctx* ctx, int32_t* device);
 /* cudaStream_t the context launches on (for callers that time with events on that stream) */

@@ -286,6 +286,28 @@ def test_gradient_gp_block_append_matches_refit(abo, orc, kind, n0, n1, d):
     assert np.array_equal(h.posterior(Xc[:5])[0], g0.gpx.posterior(Xc[:5])[0])
 
 
+def test_context_destroyed_before_its_handles(abo, orc):
+    """Finalizers of garbage-collected bindings run in arbitrary order: destroying a context orphans its live
+    handles (device memory released, calls fail cleanly, abo_gp_destroy stays valid)."""
+    c = orc.make_config("C4", n=150, m=50, d=3)
+    ctx2 = abo.Context(abo.default_context().device)
+    h = abo.GpHandle(ctx2, c["kind"], 3, 1); h.set_params(c["inv_ls"], c["scale"], c["noise"]); h.fit(c["X"], c["y"])
+    h2 = h.clone()
+    m0, _ = h.posterior(c["Xc"])
+    ctx2.close()                                                   # context first
+    for hh in (h, h2):
+        with pytest.raises(abo.AboCudaError):
+            hh.posterior(c["Xc"])
+        with pytest.raises(ValueError):
+            hh.fit(c["X"], c["y"])
+    h3 = h.clone()                                                 # a clone of an orphan is an orphan
+    for hh in (h, h2, h3):
+        hh.close()
+    # the default context is unaffected
+    g = abo.GpHandle(abo.default_context(), c["kind"], 3, 1); g.set_params(c["inv_ls"], c["scale"], c["noise"]); g.fit(c["X"], c["y"])
+    assert np.array_equal(g.posterior(c["Xc"])[0], m0)
+
+
 def test_clone_is_copy_on_write(abo, orc):
     """abo_gp_clone shares the device buffers; every writer (append, re-fit, destroy) must leave the
     other holders' posterior bit-identical (value semantics of Base.copy, StandardGP.jl:26)."""
