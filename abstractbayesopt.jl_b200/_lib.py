@@ -208,7 +208,7 @@ _default_ctx = {}
 def default_context(device: int | None = None) -> Context:
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0")) if "ABO_DEVICE" not in os.environ else int(os.environ["ABO_DEVICE"])
-    if device not in _default_ctx:
+    if device not in _default_ctx or _default_ctx[device]._h is None:      # never created, or closed by the caller
         _default_ctx[device] = Context(device)
     return _default_ctx[device]
 

@@ -412,6 +412,8 @@ def main():
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
+    del model                                      # release the device state explicitly, not at interpreter exit
+    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
