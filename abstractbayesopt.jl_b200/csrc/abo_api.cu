@@ -1065,34 +1065,58 @@ extern "C" int32_t abo_gp_posterior_cov(abo_gp* g, const double* Xc, int64_t m, 
 
 // ---- stable descending top-k with Julia isless semantics (NaN largest, -0.0 < 0.0)
 
-void topk_host(const double* s, int64_t m, int64_t k, int64_t idx_offset, std::vector<std::pair<uint64_t, int64_t>>& heap) {
-    // heap of (key, index): the WORST kept element on top.  a is worse than b if key smaller, or
-    // equal key and larger index.
-    auto worse = [](const std::pair<uint64_t, int64_t>& a, const std::pair<uint64_t, int64_t>& b) {
-        return a.first != b.first ? a.first > b.first : a.second < b.second;   // "less" for a max-heap on badness
-    };
-    for (int64_t i = 0; i < m; ++i) {
-        std::pair<uint64_t, int64_t> e(ordkey(s[i]), i + idx_offset);
-        if ((int64_t)heap.size() < k) {
-            heap.push_back(e);
-            std::push_heap(heap.begin(), heap.end(), worse);
-        } else if (worse(e, heap.front())) {       // e is better than the current worst
-            std::pop_heap(heap.begin(), heap.end(), worse);
-            heap.back() = e;
-            std::push_heap(heap.begin(), heap.end(), worse);
-        }
-    }
+// Device-side selection (kernels.cuh: sel_*): enqueue the K best of dS[0..m) on `st` into workspace slot 0 / 1, and
+// read the K (index, value) pairs back.  Nothing but K pairs crosses PCIe for the top-k.
+struct SelSlot { SelState* st; unsigned int* ties; unsigned long long* excl; long long* idx; double* val; };
+static int sel_slot(abo_ctx* c, int slot, int64_t max_m, int64_t max_k, SelSlot* out) {
+    const size_t nblk = (size_t)((max_m + SEL_CHUNK - 1) / SEL_CHUNK);
+    const size_t a0 = (sizeof(SelState) + 255) / 256 * 256, a1 = (nblk * 4 + 255) / 256 * 256, a2 = (nblk * 8 + 255) / 256 * 256,
+                 a3 = ((size_t)max_k * 8 + 255) / 256 * 256;
+    const size_t per = a0 + a1 + a2 + 2 * a3;
+    char* base;
+    int rc = ws_get(c, WS_SELECT, 2 * per, (void**)&base);
+    if (rc) return rc;
+    base += (size_t)slot * per;
+    out->st = (SelState*)base; out->ties = (unsigned int*)(base + a0); out->excl = (unsigned long long*)(base + a0 + a1);
+    out->idx = (long long*)(base + a0 + a1 + a2); out->val = (double*)(base + a0 + a1 + a2 + a3);
+    return ABO_OK;
 }
-
-static void topk_finish(std::vector<std::pair<uint64_t, int64_t>>& heap, const double* s, int64_t idx_offset,
-                        int64_t* top_idx, double* top_val) {
-    std::sort(heap.begin(), heap.end(), [](const std::pair<uint64_t, int64_t>& a, const std::pair<uint64_t, int64_t>& b) {
-        return a.first != b.first ? a.first > b.first : a.second < b.second;
-    });
-    for (size_t i = 0; i < heap.size(); ++i) {
-        top_idx[i] = heap[i].second;
-        top_val[i] = s[heap[i].second - idx_offset];
+static int device_topk_launch(abo_ctx* c, const SelSlot& q, const double* dS, int64_t m, int64_t K, cudaStream_t st) {
+    const int nblk = (int)((m + SEL_CHUNK - 1) / SEL_CHUNK);
+    const int hgrid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)c->sms * 8);
+    sel_init_kernel<<<1, 256, 0, st>>>(q.st, (long long)K);
+    KL(c);
+    for (int pass = 0; pass < 8; ++pass) {
+        sel_hist_kernel<<<hgrid, 256, 0, st>>>(dS, m, pass, q.st);
+        KL(c);
+        sel_pick_kernel<<<1, 256, 0, st>>>(q.st);
+        KL(c);
     }
+    sel_tiecount_kernel<<<nblk, 256, 0, st>>>(dS, m, q.st, q.ties);
+    KL(c);
+    sel_tiescan_kernel<<<1, 32, 0, st>>>(q.ties, nblk, q.excl);
+    KL(c);
+    sel_gather_kernel<<<nblk, 256, 0, st>>>(dS, m, q.st, q.excl, q.idx, q.val);
+    KL(c);
+    return ABO_OK;
+}
+struct TopItem { uint64_t key; int64_t idx; double val; };
+constexpr int64_t SEL_MIN_M = 65536;          // below this the host picks the K best from the read-back scores
+// copy the K pairs of a slot to the host (on `st`, synchronised) and append them with global indices
+static int device_topk_read(const SelSlot& q, int64_t K, int64_t idx_offset, std::vector<TopItem>& items, cudaStream_t st) {
+    std::vector<long long> hi((size_t)K);
+    std::vector<double> hv((size_t)K);
+    CU(cudaMemcpyAsync(hi.data(), q.idx, sizeof(long long) * K, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hv.data(), q.val, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < K; ++i) items.push_back(TopItem{ordkey(hv[(size_t)i]), (int64_t)hi[(size_t)i] + idx_offset, hv[(size_t)i]});
+    return ABO_OK;
+}
+// sortperm(rev = true) order: key descending, index ascending
+static void topk_emit(std::vector<TopItem>& items, int64_t k, int64_t* top_idx, double* top_val) {
+    std::sort(items.begin(), items.end(), [](const TopItem& a, const TopItem& b) { return a.key != b.key ? a.key > b.key : a.idx < b.idx; });
+    const int64_t cnt = std::min<int64_t>(k, (int64_t)items.size());
+    for (int64_t i = 0; i < cnt; ++i) { top_idx[i] = items[(size_t)i].idx; top_val[i] = items[(size_t)i].val; }
 }
 
 static int acq_eval_common(abo_gp* g, int acq_id, const double* params, const double* dXc, int64_t m, double* d_scores,
@@ -1103,17 +1127,32 @@ static int acq_eval_common(abo_gp* g, int acq_id, const double* params, const do
     double* dS = d_scores;
     if (!dS && (rc = ws_get(c, WS_OUT_A, sizeof(double) * (size_t)m, (void**)&dS))) return rc;
     if ((rc = sweep_device(g, dXc, m, 0, acq_id, params, nullptr, nullptr, dS))) return rc;
-    if (h_scores || k > 0) {
+    const int64_t K = std::min(k, m);
+    if (K > 0 && m <= SEL_MIN_M) {
+        // small sets (the 10 000-point grid of optimize_acquisition): the 19 selection launches would cost more than
+        // reading 8 m bytes back; pick the K best on the host
         double* hs = h_scores;
         if (!hs) { if ((rc = pinned_get(c, sizeof(double) * (size_t)m, (void**)&hs))) return rc; }
         CU(cudaMemcpyAsync(hs, dS, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if (k > 0) {
-            std::vector<std::pair<uint64_t, int64_t>> heap;
-            heap.reserve((size_t)std::min(k, m) + 1);
-            topk_host(hs, m, std::min(k, m), 0, heap);
-            topk_finish(heap, hs, 0, top_idx, top_val);
-        }
+        std::vector<TopItem> items((size_t)m);
+        for (int64_t i = 0; i < m; ++i) items[(size_t)i] = TopItem{ordkey(hs[i]), i, hs[i]};
+        auto better = [](const TopItem& a, const TopItem& b) { return a.key != b.key ? a.key > b.key : a.idx < b.idx; };
+        std::partial_sort(items.begin(), items.begin() + K, items.end(), better);
+        for (int64_t i = 0; i < K; ++i) { top_idx[i] = items[(size_t)i].idx; top_val[i] = items[(size_t)i].val; }
+        return ABO_OK;
+    }
+    SelSlot q{};
+    if (K > 0) {
+        if ((rc = sel_slot(c, 0, m, K, &q))) return rc;
+        if ((rc = device_topk_launch(c, q, dS, m, K, st))) return rc;
+    }
+    if (h_scores) CU(cudaMemcpyAsync(h_scores, dS, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    if (K > 0) {
+        std::vector<TopItem> items;
+        items.reserve((size_t)K);
+        if ((rc = device_topk_read(q, K, 0, items, st))) return rc;
+        topk_emit(items, K, top_idx, top_val);
     } else {
         CU(cudaStreamSynchronize(st));
     }
@@ -1132,7 +1171,8 @@ static int acq_check(abo_gp* g, int acq_id, const double* params, const void* Xc
 
 // Large host candidate sets go through in pieces so that the copies hide behind the sweep: while piece i
 // is being evaluated the host stages piece i+1 (H2D on the copy stream), then reads back the results of
-// piece i-1 (and feeds the scores to the top-k heap).  Per-candidate results do not depend on the piece size.
+// piece i-1 (scores if asked for, and the K best of the piece, selected on the device).  Per-candidate results
+// do not depend on the piece size.
 // acq_id < 0: posterior mean / variance of output 0 (h_mean / h_var, each may be NULL).
 static int64_t host_piece() {
     static const int64_t piece = getenv("ABO_ACQ_PIECE") ? atoll(getenv("ABO_ACQ_PIECE")) : 262144;
@@ -1150,21 +1190,23 @@ static int sweep_host_pieces(abo_gp* g, const double* Xc, int64_t m, int acq_id,
     if ((rc = ws_get(c, WS_CAND, sizeof(double) * (size_t)m * d, (void**)&dXc))) return rc;
     if ((rc = ws_get(c, WS_OUT_A, sizeof(double) * (size_t)m, (void**)&dA))) return rc;
     if (acq_id < 0 && (rc = ws_get(c, WS_OUT_B, sizeof(double) * (size_t)m, (void**)&dB))) return rc;
-    double* hs = h_scores;                               // acquisition: dA = scores; posterior: dA = mean, dB = variance
-    if (acq_id >= 0 && k > 0 && !hs) { if ((rc = pinned_get(c, sizeof(double) * (size_t)m, (void**)&hs))) return rc; }
-    std::vector<std::pair<uint64_t, int64_t>> heap;
-    if (k > 0) heap.reserve((size_t)std::min(k, m) + 1);
+    // acquisition: dA = scores; posterior: dA = mean, dB = variance
+    const int64_t Kp = (acq_id >= 0 && k > 0) ? std::min(k, piece) : 0;      // per piece: its own K best, selected on the device
+    SelSlot slot[2] = {};
+    if (Kp > 0) { if ((rc = sel_slot(c, 0, piece, Kp, &slot[0])) || (rc = sel_slot(c, 1, piece, Kp, &slot[1]))) return rc; }
+    std::vector<TopItem> items;
+    if (Kp > 0) items.reserve((size_t)(Kp * np));
     auto off = [&](int64_t i) { return i * piece; };
     auto cnt = [&](int64_t i) { return std::min(piece, m - i * piece); };
-    auto drain = [&](int64_t i) -> int {                 // results of piece i -> host, top-k heap
-        double* hosts[2] = {acq_id >= 0 ? hs : h_mean, acq_id >= 0 ? nullptr : h_var};
+    auto drain = [&](int64_t i) -> int {                 // results of piece i -> host
+        double* hosts[2] = {acq_id >= 0 ? h_scores : h_mean, acq_id >= 0 ? nullptr : h_var};
         double* devs[2] = {dA, dB};
-        if (!hosts[0] && !hosts[1]) return ABO_OK;
+        if (!hosts[0] && !hosts[1] && Kp == 0) return ABO_OK;
         CU(cudaStreamWaitEvent(sc, c->ev_pc[i & 1], 0));
         for (int q = 0; q < 2; ++q)
             if (hosts[q]) CU(cudaMemcpyAsync(hosts[q] + off(i), devs[q] + off(i), sizeof(double) * cnt(i), cudaMemcpyDeviceToHost, sc));
+        if (Kp > 0) return device_topk_read(slot[i & 1], std::min(Kp, cnt(i)), off(i), items, sc);
         CU(cudaStreamSynchronize(sc));
-        if (k > 0) topk_host(hs + off(i), cnt(i), std::min(k, m), off(i), heap);
         return ABO_OK;
     };
     CU(cudaMemcpyAsync(dXc, Xc, sizeof(double) * cnt(0) * d, cudaMemcpyHostToDevice, sc));
@@ -1174,6 +1216,7 @@ static int sweep_host_pieces(abo_gp* g, const double* Xc, int64_t m, int acq_id,
         if (acq_id >= 0) rc = sweep_device(g, dXc + off(i) * d, cnt(i), 0, acq_id, params, nullptr, nullptr, dA + off(i));
         else rc = sweep_device(g, dXc + off(i) * d, cnt(i), 0, -1, nullptr, dA + off(i), dB + off(i), nullptr);
         if (rc) return rc;
+        if (Kp > 0 && (rc = device_topk_launch(c, slot[i & 1], dA + off(i), cnt(i), std::min(Kp, cnt(i)), st))) return rc;
         CU(cudaEventRecord(c->ev_pc[i & 1], st));
         if (i + 1 < np) {
             CU(cudaMemcpyAsync(dXc + off(i + 1) * d, Xc + off(i + 1) * d, sizeof(double) * cnt(i + 1) * d, cudaMemcpyHostToDevice, sc));
@@ -1183,7 +1226,7 @@ static int sweep_host_pieces(abo_gp* g, const double* Xc, int64_t m, int acq_id,
     }
     if ((rc = drain(np - 1))) return rc;
     CU(cudaStreamSynchronize(st));
-    if (k > 0) topk_finish(heap, hs, 0, top_idx, top_val);
+    if (Kp > 0) topk_emit(items, std::min(k, m), top_idx, top_val);
     return ABO_OK;
 }
 

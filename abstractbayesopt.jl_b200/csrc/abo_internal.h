@@ -31,7 +31,7 @@ int abo_fail(int code, const char* fmt, ...);
 enum WsSlot {
     WS_STAGE_X = 0, WS_STAGE_Y, WS_DINV, WS_INFO, WS_TRTRI, WS_VEC_PART, WS_KS, WS_PMEAN, WS_SUMSQ, WS_CAND,
     WS_OUT_A, WS_OUT_B, WS_NLML_K, WS_NLML_LINV, WS_NLML_W, WS_NLML_X, WS_NLML_VEC, WS_NLML_PAR, WS_APPEND,
-    WS_TOPK, WS_GRAD_W, WS_GRAD_Z, WS_GRAD_PART, WS_GRAD_OUT, WS_COUNT
+    WS_TOPK, WS_SELECT, WS_GRAD_W, WS_GRAD_Z, WS_GRAD_PART, WS_GRAD_OUT, WS_COUNT
 };
 
 struct WsBuf { void* ptr = nullptr; size_t bytes = 0; };
@@ -98,8 +98,6 @@ int trtri_blocked(abo_ctx* c, const double* L, double* Linv, double* W, int64_t 
                   const double* Dinv, int64_t strideD, int batch);
 int solve_alpha(abo_ctx* c, const double* Linv, int64_t ld, int64_t N, const double* delta, double* beta,
                 double* alpha, int64_t strideM, int64_t strideV, int batch);
-void topk_host(const double* s, int64_t m, int64_t k, int64_t idx_offset,
-               std::vector<std::pair<uint64_t, int64_t>>& heap);
 void abo_nccl_teardown(abo_ctx* c);
 int prof_mark(abo_ctx* c);
 int prof_collect(abo_ctx* c);

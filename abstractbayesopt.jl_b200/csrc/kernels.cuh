@@ -1195,6 +1195,130 @@ __global__ void __launch_bounds__(256) nlml_finish_kernel(const double* __restri
 }  // namespace abo
 
 // ------------------------------------------------------------------------------------------
+// Device-side stable top-k of the scores: sortperm(scores; rev = true)[1:k] (acq_utils.jl:51-52) as an exact radix
+// select on the 64-bit order keys (Julia isless: NaN largest, -0.0 < 0.0), ties resolved by the smaller index.
+//   8 x (digit histogram over the elements matching the prefix found so far, pick the digit that contains the
+//   k-th largest)  ->  threshold key T and r = how many elements equal to T are still needed
+//   tie ranks in index order (per-chunk counts, exclusive scan)  ->  gather {key > T} and the first r of {key == T}
+// The K selected (index, value) pairs come back unordered; the caller sorts K items.
+// ------------------------------------------------------------------------------------------
+namespace abo {
+struct SelState {
+    unsigned long long prefix;        // high digits of the threshold key found so far
+    long long remaining;              // how many of the elements matching the prefix are still needed
+    unsigned long long hist[256];
+    unsigned int out_count;
+    unsigned int pad;
+};
+constexpr int SEL_CHUNK = 4096;       // elements per block in the tie / gather passes (256 threads x 16 consecutive)
+
+__device__ __forceinline__ unsigned long long ordkey_dev(double v) {
+    if (v != v) return ~0ull;
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__global__ void sel_init_kernel(SelState* st, long long k) {
+    const int t = threadIdx.x;
+    if (t < 256) st->hist[t] = 0;
+    if (t == 0) { st->prefix = 0; st->remaining = k; st->out_count = 0; }
+}
+__global__ void __launch_bounds__(256) sel_hist_kernel(const double* __restrict__ s, int64_t m, int pass, SelState* st) {
+    __shared__ unsigned int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int shift = 56 - 8 * pass;
+    const unsigned long long prefix = st->prefix;
+    for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < m; i += (int64_t)gridDim.x * 256) {
+        const unsigned long long key = ordkey_dev(s[i]);
+        if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&sh[(unsigned)(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+__global__ void sel_pick_kernel(SelState* st) {
+    if (threadIdx.x == 0) {
+        long long rem = st->remaining, cum = 0;
+        int dgt = 255;
+        for (; dgt > 0; --dgt) {
+            const long long cnt = (long long)st->hist[dgt];
+            if (cum + cnt >= rem) break;
+            cum += cnt;
+        }
+        st->prefix = (st->prefix << 8) | (unsigned long long)dgt;
+        st->remaining = rem - cum;
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) st->hist[threadIdx.x] = 0;
+}
+// ties[b] = number of elements equal to the threshold key in chunk b
+__global__ void __launch_bounds__(256) sel_tiecount_kernel(const double* __restrict__ s, int64_t m, const SelState* st,
+                                                           unsigned int* __restrict__ ties) {
+    __shared__ unsigned int sh[256];
+    const unsigned long long T = st->prefix;
+    const int64_t base = (int64_t)blockIdx.x * SEL_CHUNK + threadIdx.x * 16;
+    unsigned int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int64_t i = base + q;
+        if (i < m && ordkey_dev(s[i]) == T) ++cnt;
+    }
+    sh[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ties[blockIdx.x] = sh[0];
+}
+// in-place exclusive scan of the chunk counts (64-bit running sum kept in registers; one thread: <= a few thousand chunks)
+__global__ void sel_tiescan_kernel(unsigned int* ties, int nblk, unsigned long long* excl) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int b = 0; b < nblk; ++b) { excl[b] = run; run += ties[b]; }
+    }
+}
+__global__ void __launch_bounds__(256) sel_gather_kernel(const double* __restrict__ s, int64_t m, SelState* st,
+                                                         const unsigned long long* __restrict__ excl,
+                                                         long long* __restrict__ out_idx, double* __restrict__ out_val) {
+    __shared__ unsigned int sh[256];
+    const unsigned long long T = st->prefix;
+    const unsigned long long need = (unsigned long long)st->remaining;      // ties to take, in index order
+    const int64_t base = (int64_t)blockIdx.x * SEL_CHUNK + threadIdx.x * 16;
+    double v[16];
+    unsigned int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int64_t i = base + q;
+        v[q] = (i < m) ? s[i] : 0.0;
+        if (i < m && ordkey_dev(v[q]) == T) ++cnt;
+    }
+    sh[threadIdx.x] = cnt;
+    __syncthreads();
+    // exclusive scan over the 256 threads (Hillis-Steele on the shared array)
+    for (int o = 1; o < 256; o <<= 1) {
+        unsigned int add = ((int)threadIdx.x >= o) ? sh[threadIdx.x - o] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += add;
+        __syncthreads();
+    }
+    unsigned long long rank = excl[blockIdx.x] + (unsigned long long)(sh[threadIdx.x] - cnt);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int64_t i = base + q;
+        if (i >= m) break;
+        const unsigned long long key = ordkey_dev(v[q]);
+        bool take = key > T;
+        if (key == T) { take = rank < need; ++rank; }
+        if (take) {
+            const unsigned int pos = atomicAdd(&st->out_count, 1u);
+            out_idx[pos] = (long long)i;
+            out_val[pos] = v[q];
+        }
+    }
+}
+}  // namespace abo
+
+// ------------------------------------------------------------------------------------------
 // acquisition value AND gradient for a small batch of points (batched local refinement of
 // optimize_acquisition, src/acquisition_functions/acq_utils.jl:55-71, which the reference drives
 // with finite differences of single-point evaluations):

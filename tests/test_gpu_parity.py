@@ -128,6 +128,34 @@ def test_topk_ties_and_nan_order(abo, orc):
     assert np.array_equal(scores[:50], scores[50:100])
 
 
+@pytest.mark.parametrize("m_big,k", [(70_000, 64), (600_000, 100), (300_001, 5000)])
+def test_device_selection_ties_nan_and_piece_merge(abo, orc, m_big, k):
+    """Above 65 536 candidates the K best are selected on the device (radix select on the order keys) and, above
+    262 144, per piece with a merge: same list as sortperm(scores; rev = true)[1:k] with heavy ties (a block of
+    300 candidates repeated all over the set, so the threshold key itself is tied across pieces) and NaN scores
+    (NaN sorts first, Julia isless)."""
+    c = orc.make_config("C1", n=20, m=300)
+    gp = abo.update(abo.StandardGP(make_kernel(abo, 0, c["inv_ls"], 1.0), 1e-6), c["X"], c["y"])
+    reps = -(-m_big // 300)
+    Xc = np.tile(c["Xc"], (reps, 1))[:m_big].copy()
+    Xc[[7, 123_45 % m_big, m_big - 3]] = np.nan                   # NaN coordinates -> NaN scores
+    for acq in (abo.UpperConfidenceBound(2.0), abo.ExpectedImprovement(0.01, float(np.min(c["y"])))):
+        scores, ti, tv = acq.topk(gp, Xc, k)
+        assert np.isnan(scores[[7, 123_45 % m_big, m_big - 3]]).all()
+        ref = orc.sortperm_rev(scores, k)
+        assert list(ti) == list(ref)
+        assert np.array_equal(tv, scores[ti], equal_nan=True)
+    # device-resident candidates through abo_acq_eval_dev (no pieces): same selection
+    import torch
+    dX = torch.from_numpy(Xc).cuda()
+    dS = torch.empty(m_big, dtype=torch.float64, device="cuda")
+    acq = abo.UpperConfidenceBound(2.0)
+    ti2, tv2 = gp.gpx.acq_eval_dev(acq.acq_id, acq.params(), dX.data_ptr(), m_big, dS.data_ptr(), k)
+    torch.cuda.synchronize()
+    sc = dS.cpu().numpy()
+    assert list(ti2) == list(orc.sortperm_rev(sc, k))
+
+
 def test_edge_sizes(abo, orc):
     c = orc.make_config("C2", n=200, m=300)
     gp = abo.update(abo.StandardGP(make_kernel(abo, 1, c["inv_ls"], 1.0), c["noise"]), c["X"], c["y"])
