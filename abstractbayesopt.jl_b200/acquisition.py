@@ -30,10 +30,12 @@ class AbstractAcquisition:
         h = _need_posterior(surrogate)
         return h.acq_eval_grad(self.acq_id, self.params(), _as_points(x, h.d))
 
-    def topk(self, surrogate, x, k):
-        """scores and sortperm(scores; rev=true)[1:k] (acq_utils.jl:50-52) in one call; 0-based."""
+    def topk(self, surrogate, x, k, want_scores=True):
+        """scores and sortperm(scores; rev=true)[1:k] (acq_utils.jl:50-52) in one call; 0-based.
+        want_scores=False returns None for the scores: only the k selected (index, value) pairs
+        leave the device."""
         h = _need_posterior(surrogate)
-        return h.acq_eval(self.acq_id, self.params(), _as_points(x, h.d), k=k)
+        return h.acq_eval(self.acq_id, self.params(), _as_points(x, h.d), k=k, want_scores=want_scores)
 
 
 @dataclass(frozen=True)
@@ -107,7 +109,7 @@ class GradientNormUCB(AbstractAcquisition):
                 out[c0 + c] = -mu_sq + self.beta * np.sqrt(max(var_sq, 1e-12))
         return out
 
-    def topk(self, surrogate, x, k):
+    def topk(self, surrogate, x, k, want_scores=True):
         s = self(surrogate, x)
         ti, tv = merge_topk([np.arange(len(s))], [s], k)
         return s, ti, tv
@@ -134,7 +136,7 @@ class EnsembleAcquisition(AbstractAcquisition):
     def __call__(self, surrogate, x):
         return sum(w * a(surrogate, x) for w, a in zip(self.weights, self.acquisitions))
 
-    def topk(self, surrogate, x, k):
+    def topk(self, surrogate, x, k, want_scores=True):
         s = self(surrogate, x)
         ti, tv = merge_topk([np.arange(len(s))], [s], k)
         return s, ti, tv

@@ -61,7 +61,7 @@ def optimize_acquisition(acqf, surrogate, domain, n_grid=10_000, n_local=100, rn
     finite-difference scheme (SciPy L-BFGS-B); refine=False returns the best grid point."""
     rng = np.random.default_rng() if rng is None else rng
     grid = latin_hypercube(n_grid, domain.lower, domain.upper, rng)
-    _, top_idx, top_val = acqf.topk(surrogate, grid, n_local)
+    _, top_idx, top_val = acqf.topk(surrogate, grid, n_local, want_scores=False)
     starts = grid[top_idx]
     if refine is False or len(starts) == 0:
         return np.array(starts[0])

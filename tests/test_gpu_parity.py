@@ -145,6 +145,9 @@ def test_device_selection_ties_nan_and_piece_merge(abo, orc, m_big, k):
         ref = orc.sortperm_rev(scores, k)
         assert list(ti) == list(ref)
         assert np.array_equal(tv, scores[ti], equal_nan=True)
+    none, ti3, tv3 = abo.UpperConfidenceBound(2.0).topk(gp, Xc, k, want_scores=False)     # only K pairs cross PCIe
+    s_full, ti4, _ = abo.UpperConfidenceBound(2.0).topk(gp, Xc, k)
+    assert none is None and list(ti3) == list(ti4) and np.array_equal(tv3, s_full[ti4], equal_nan=True)
     # device-resident candidates through abo_acq_eval_dev (no pieces): same selection
     import torch
     dX = torch.from_numpy(Xc).cuda()
