@@ -121,7 +121,10 @@ int32_t abo_gp_posterior_cov(abo_gp* gp, const double* Xc, int64_t m, int32_t ou
 
 /* fused acquisition sweep: scores = acq(surrogate, Xc) (ExpectedImprovement.jl:40-45 etc.) and
  * sortperm(scores; rev=true)[1:k] (acq_utils.jl:50-52): stable, descending, NaN first.
- * scores (m) may be NULL; k may be 0 (top_idx/top_val then unused). */
+ * scores (m) may be NULL — then only the k selected (index, value) pairs leave the device (the
+ * selection is an exact radix select on the GPU; below 65 536 candidates the host picks them from
+ * the read-back scores); k may be 0 (top_idx/top_val then unused).  Host candidate sets above
+ * 262 144 points are staged, evaluated and read back in overlapped pieces. */
 int32_t abo_acq_eval(abo_gp* gp, int32_t acq_id, const double* params, const double* Xc, int64_t m,
                      double* scores, int64_t k, int64_t* top_idx, double* top_val);
 /* same, candidates already resident in HBM (d_Xc: m*d doubles, point-major); d_scores (device,
