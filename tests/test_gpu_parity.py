@@ -128,7 +128,7 @@ def test_topk_ties_and_nan_order(abo, orc):
     assert np.array_equal(scores[:50], scores[50:100])
 
 
-@pytest.mark.parametrize("m_big,k", [(70_000, 64), (600_000, 100), (300_001, 5000)])
+@pytest.mark.parametrize("m_big,k", [(70_000, 64), (600_000, 100), (300_001, 5000), (66_001, 66_001), (65_537, 1)])
 def test_device_selection_ties_nan_and_piece_merge(abo, orc, m_big, k):
     """Above 65 536 candidates the K best are selected on the device (radix select on the order keys) and, above
     262 144, per piece with a merge: same list as sortperm(scores; rev = true)[1:k] with heavy ties (a block of
