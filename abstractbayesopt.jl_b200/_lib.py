@@ -19,7 +19,7 @@ SYMBOLS = [
     "abo_ctx_launch_count", "abo_ctx_profile", "abo_ctx_profile_read", "abo_debug_potf2_clocks", "abo_gp_create", "abo_gp_destroy", "abo_gp_set_params", "abo_gp_fit", "abo_gp_append",
     "abo_gp_clone", "abo_gp_n", "abo_gp_alpha", "abo_gp_factor", "abo_gp_posterior", "abo_gp_posterior_cov", "abo_acq_eval", "abo_acq_eval_dev", "abo_acq_eval_grad",
     "abo_nlml_batch", "abo_potrf_dev", "abo_fill_distance", "abo_nccl_unique_id", "abo_ctx_init_rank", "abo_gp_sync",
-    "abo_topk_allgather", "abo_allgather_f64",
+    "abo_topk_allgather", "abo_allgather_f64", "abo_ctx_ranks", "abo_ctx_trim",
 ]
 
 
@@ -58,6 +58,7 @@ def lib():
         sigs = {
             "abo_ctx_create": [i32, C.POINTER(vp)],
             "abo_ctx_destroy": [vp],
+            "abo_ctx_trim": [vp],
             "abo_ctx_device": [vp, C.POINTER(i32)],
             "abo_ctx_stream": [vp, C.POINTER(vp)],
             "abo_ctx_launch_count": [vp, C.POINTER(i64)],
@@ -86,6 +87,7 @@ def lib():
             "abo_gp_sync": [vp, i32],
             "abo_topk_allgather": [vp, i64, i64, vp, vp, C.POINTER(i64)],
             "abo_allgather_f64": [vp, vp, i64, vp],
+            "abo_ctx_ranks": [vp, C.POINTER(i32), C.POINTER(i32)],
         }
         for name, args in sigs.items():
             f = getattr(L, name)
@@ -168,6 +170,16 @@ class Context:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         check(lib().abo_ctx_init_rank(self._h, rank, nranks, buf))
 
+    def trim(self):
+        """Release the pooled posterior buffer sets and workspaces the context keeps between calls."""
+        check(lib().abo_ctx_trim(self._h))
+
+    def ranks(self):
+        """(rank, nranks) of the context's NCCL communicator; (0, 1) without one."""
+        r = C.c_int32(0); n = C.c_int32(1)
+        check(lib().abo_ctx_ranks(self._h, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
     def topk_allgather(self, k, idx, val):
         """NCCL all-gather + merge of per-rank (global index, value) top-k lists."""
         ti = np.zeros(k, dtype=np.int64); tv = np.zeros(k)
@@ -180,6 +192,9 @@ class Context:
     def allgather_f64(self, send, nranks: int):
         """NCCL all-gather of equally sized float64 blocks; returns an (nranks, len(send)) array."""
         send = f64(np.ravel(send))
+        if self.ranks()[1] != nranks:
+            raise AboCudaError(f"allgather_f64 over {nranks} ranks, but the context's NCCL communicator spans "
+                               f"{self.ranks()[1]} (call init_nccl_context first)")
         recv = np.empty((nranks, send.size))
         check(lib().abo_allgather_f64(self._h, ptr(send), send.size, ptr(recv)))
         return recv

@@ -289,6 +289,6 @@ def optimize(BO: BOStruct, standardize="mean_scale", hyper_params="all", num_res
         y = y + math.sqrt(BO.noise) / s0 * rng.standard_normal(y.shape) if BO.noise > 0 else y
         BO.ys_non_std.append(y)
         y_std = (y - mu) / s0 if isinstance(BO.model, GradientGP) else (y - mu) / sd
-        BO = update_bo(BO, x_cand, y_std, i)
-        i += 1
+        i += 1                                           # incremented BEFORE update(BO, ...) (bayesian_opt.jl:441-445):
+        BO = update_bo(BO, x_cand, y_std, i)             # BO.iter = i + 1, so exactly max_iter passes run
     return BO, acq_list, (mu, sd)

@@ -60,6 +60,22 @@ static int configure_kernels() {
     return ABO_OK;
 }
 
+static int ctx_init_resources(abo_ctx* c) {
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));    // main / panel stream
+    CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));   // look-ahead trailing updates
+    CU(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_hi));   // bulk half of the panel chain / copy stream
+    for (int q = 0; q < 3; ++q) CU(cudaEventCreateWithFlags(&c->ev_p[q], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+    for (int q = 0; q < 2; ++q) {
+        CU(cudaEventCreateWithFlags(&c->ev_h2d[q], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_pc[q], cudaEventDisableTiming));
+    }
+    return configure_kernels();
+}
+
 extern "C" int32_t abo_ctx_create(int32_t device, abo_ctx** out) {
     if (!out) return abo_fail(ABO_ERR_INVALID, "abo_ctx_create: out is NULL");
     int ndev = 0;
@@ -78,30 +94,23 @@ extern "C" int32_t abo_ctx_create(int32_t device, abo_ctx** out) {
     if (!c) return abo_fail(ABO_ERR_ALLOC, "host allocation failed");
     c->device = device;
     c->sms = prop.multiProcessorCount;
-    int prio_lo = 0, prio_hi = 0;
-    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));    // main / panel stream
-    CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));   // look-ahead trailing updates
-    CU(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_hi));   // bulk half of the panel chain
-    for (int q = 0; q < 3; ++q) CU(cudaEventCreateWithFlags(&c->ev_p[q], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
-    for (int q = 0; q < 2; ++q) {
-        CU(cudaEventCreateWithFlags(&c->ev_h2d[q], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&c->ev_pc[q], cudaEventDisableTiming));
-    }
-    int rc = configure_kernels();
-    if (rc) return rc;
+    int rc = ctx_init_resources(c);
+    if (rc) { abo_ctx_destroy(c); return rc; }           // streams / events created so far are released (last error kept)
     *out = c;
     return ABO_OK;
 }
 
 static void gp_free_device(abo_gp* g);
+// every stream of the context: workspace slots and caller buffers may be in use on any of them
+void ctx_sync_all(abo_ctx* c) {
+    for (cudaStream_t s_ : {c->stream, c->stream2, c->stream3}) if (s_) cudaStreamSynchronize(s_);
+}
 
 extern "C" int32_t abo_ctx_destroy(abo_ctx* c) {
     if (!c) return ABO_OK;
+    const std::string keep = g_err;                      // a failing abo_ctx_create reports ITS error, not a teardown one
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    ctx_sync_all(c);
     for (abo_gp* g : c->live) { gp_free_device(g); g->ctx = nullptr; }   // orphaned: only abo_gp_destroy is valid on them
     c->live.clear();
     for (auto& b : c->ws) if (b.ptr) cudaFree(b.ptr);
@@ -109,14 +118,25 @@ extern "C" int32_t abo_ctx_destroy(abo_ctx* c) {
     for (auto e : c->prof_events) cudaEventDestroy(e);
     if (c->pinned) cudaFreeHost(c->pinned);
     abo_nccl_teardown(c);
-    cudaEventDestroy(c->ev_a);
-    cudaEventDestroy(c->ev_b);
-    for (int q = 0; q < 2; ++q) { cudaEventDestroy(c->ev_h2d[q]); cudaEventDestroy(c->ev_pc[q]); }
-    cudaStreamDestroy(c->stream);
-    cudaStreamDestroy(c->stream2);
-    cudaStreamDestroy(c->stream3);
-    for (int q = 0; q < 3; ++q) cudaEventDestroy(c->ev_p[q]);
+    auto ev_free = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
+    ev_free(c->ev_a); ev_free(c->ev_b);
+    for (int q = 0; q < 2; ++q) { ev_free(c->ev_h2d[q]); ev_free(c->ev_pc[q]); }
+    for (cudaStream_t s_ : {c->stream, c->stream2, c->stream3}) if (s_) cudaStreamDestroy(s_);
+    for (int q = 0; q < 3; ++q) ev_free(c->ev_p[q]);
+    cudaGetLastError();
     delete c;
+    g_err = keep;
+    return ABO_OK;
+}
+
+// release every cached device buffer of the context (pooled posterior sets, workspaces, pinned staging)
+extern "C" int32_t abo_ctx_trim(abo_ctx* c) {
+    if (!c) return abo_fail(ABO_ERR_INVALID, "null ctx");
+    CU(cudaSetDevice(c->device));
+    ctx_sync_all(c);
+    gp_pool_clear(c);
+    for (auto& b : c->ws) if (b.ptr) { cudaFree(b.ptr); b.ptr = nullptr; b.bytes = 0; }
+    if (c->pinned) { cudaFreeHost(c->pinned); c->pinned = nullptr; c->pinned_bytes = 0; }
     return ABO_OK;
 }
 
@@ -222,7 +242,7 @@ extern "C" int32_t abo_debug_potf2_clocks(abo_ctx* c, int64_t out[16]) {
 int ws_get(abo_ctx* c, int slot, size_t bytes, void** out) {
     auto& b = c->ws[slot];
     if (b.bytes < bytes) {
-        if (b.ptr) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(b.ptr)); b.ptr = nullptr; b.bytes = 0; }
+        if (b.ptr) { ctx_sync_all(c); CU(cudaFree(b.ptr)); b.ptr = nullptr; b.bytes = 0; }
         cudaError_t e = cudaMalloc(&b.ptr, bytes);
         if (e != cudaSuccess) { cudaGetLastError(); return abo_fail(ABO_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
         b.bytes = bytes;
@@ -233,12 +253,12 @@ int ws_get(abo_ctx* c, int slot, size_t bytes, void** out) {
 
 void ws_release(abo_ctx* c, int slot) {
     auto& b = c->ws[slot];
-    if (b.ptr) { cudaStreamSynchronize(c->stream); cudaFree(b.ptr); b.ptr = nullptr; b.bytes = 0; }
+    if (b.ptr) { ctx_sync_all(c); cudaFree(b.ptr); b.ptr = nullptr; b.bytes = 0; }
 }
 
 int pinned_get(abo_ctx* c, size_t bytes, void** out) {
     if (c->pinned_bytes < bytes) {
-        if (c->pinned) { CU(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->pinned); c->pinned = nullptr; c->pinned_bytes = 0; }
+        if (c->pinned) { ctx_sync_all(c); cudaFreeHost(c->pinned); c->pinned = nullptr; c->pinned_bytes = 0; }
         cudaError_t e = cudaMallocHost(&c->pinned, bytes);
         if (e != cudaSuccess) { cudaGetLastError(); return abo_fail(ABO_ERR_ALLOC, "cudaMallocHost(%zu) failed", bytes); }
         c->pinned_bytes = bytes;
@@ -1178,8 +1198,23 @@ static int64_t host_piece() {
     static const int64_t piece = getenv("ABO_ACQ_PIECE") ? atoll(getenv("ABO_ACQ_PIECE")) : 262144;
     return piece;
 }
+static int sweep_host_pieces_run(abo_gp* g, const double* Xc, int64_t m, int acq_id, const double* params, double* h_mean,
+                                 double* h_var, double* h_scores, int64_t k, int64_t* top_idx, double* top_val);
 static int sweep_host_pieces(abo_gp* g, const double* Xc, int64_t m, int acq_id, const double* params, double* h_mean,
                              double* h_var, double* h_scores, int64_t k, int64_t* top_idx, double* top_val) {
+    const int rc = sweep_host_pieces_run(g, Xc, m, acq_id, params, h_mean, h_var, h_scores, k, top_idx, top_val);
+    if (rc) {
+        // an error return must not leave copies or kernels in flight that target the caller's host buffers or the
+        // workspace slots (the next call may re-allocate them): drain both streams, keep the first error message
+        const std::string keep = g_err;
+        ctx_sync_all(g->ctx);
+        cudaGetLastError();
+        g_err = keep;
+    }
+    return rc;
+}
+static int sweep_host_pieces_run(abo_gp* g, const double* Xc, int64_t m, int acq_id, const double* params, double* h_mean,
+                                 double* h_var, double* h_scores, int64_t k, int64_t* top_idx, double* top_val) {
     abo_ctx* c = g->ctx;
     cudaStream_t st = c->stream, sc = c->stream3;
     const int d = g->d;

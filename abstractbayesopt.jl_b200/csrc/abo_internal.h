@@ -89,6 +89,7 @@ int gp_alloc(abo_gp* g, int64_t Npad, int64_t ldx);
 int gp_unshare(abo_gp* g);
 void gp_pool_clear(abo_ctx* c);
 static inline bool gp_shared(const abo_gp* g) { return g->share && *g->share > 1; }
+void ctx_sync_all(abo_ctx* c);
 void ws_release(abo_ctx* c, int slot);
 int ws_get(abo_ctx* c, int slot, size_t bytes, void** out);
 int pinned_get(abo_ctx* c, size_t bytes, void** out);

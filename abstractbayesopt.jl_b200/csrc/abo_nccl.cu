@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <string>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -101,39 +102,108 @@ static int bcast_doubles(abo_ctx* c, std::vector<double>& h, int root) {
     return ABO_OK;
 }
 
+// every rank contributes one status word; returns the first non-zero one (rank order) in *worst — the outcome of a
+// multi-rank call must be COLLECTIVE: a rank that bails out alone leaves its peers blocked inside the next collective
+static int gather_status(abo_ctx* c, int mine, int* worst, int* worst_rank) {
+    double* d;
+    int rc = ws_get(c, WS_TOPK, sizeof(double) * (size_t)(c->nranks + 1), (void**)&d);
+    if (rc) return rc;
+    double v = (double)mine;
+    CU(cudaMemcpyAsync(d, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NC(nccl().allGather(d, d + 1, 1, NCCL_FLOAT64, c->nccl_comm, c->stream));
+    std::vector<double> all((size_t)c->nranks);
+    CU(cudaMemcpyAsync(all.data(), d + 1, sizeof(double) * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *worst = 0; *worst_rank = -1;
+    for (int r = 0; r < c->nranks; ++r)
+        if ((int)all[r] != 0) { *worst = (int)all[r]; *worst_rank = r; break; }
+    return ABO_OK;
+}
+
+// lower tiles (incl. the diagonal ones) of an Npad x Npad row-major matrix <-> a packed buffer of T(T+1)/2 tiles
+// (tile (i, j), j <= i, at slot i(i+1)/2 + j; 128 x 128 row-major inside).  The posterior broadcast ships packed
+// lower triangles: the upper tiles of L and L^-1 are never read by any kernel.
+__global__ void pack_lower_tiles_kernel(const double* __restrict__ M, int64_t ld, double* __restrict__ packed, int unpack) {
+    const int i = blockIdx.y, j = blockIdx.x;
+    if (j > i) return;
+    double* tile = packed + ((int64_t)i * (i + 1) / 2 + j) * 128 * 128;
+    const double* src = M + (int64_t)i * 128 * ld + (int64_t)j * 128;
+    for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
+        const int r = e >> 6, c2 = e & 63;
+        if (unpack) reinterpret_cast<double2*>(const_cast<double*>(src) + (int64_t)r * ld)[c2] = reinterpret_cast<const double2*>(tile + r * 128)[c2];
+        else reinterpret_cast<double2*>(tile + r * 128)[c2] = reinterpret_cast<const double2*>(src + (int64_t)r * ld)[c2];
+    }
+}
+
 extern "C" int32_t abo_gp_sync(abo_gp* g, int32_t root) {
     if (!g) return abo_fail(ABO_ERR_INVALID, "null gp");
     if (!g->ctx) return abo_fail(ABO_ERR_INVALID, "the context of this handle has been destroyed");
     abo_ctx* c = g->ctx;
     if (c->nranks == 1) return ABO_OK;
     if (!c->nccl_comm) return abo_fail(ABO_ERR_NCCL, "context has no NCCL communicator (abo_ctx_init_rank)");
+    if (root < 0 || root >= c->nranks) return abo_fail(ABO_ERR_INVALID, "root %d out of range", root);
     CU(cudaSetDevice(c->device));
+    // ---- header: ALWAYS broadcast, with the root's own status in it (h[11]) — an un-fitted root must not return
+    //      before the collective its peers are already waiting in
     const int HN = 16 + 64;
     std::vector<double> h(HN, 0.0);
     if (c->rank == root) {
-        if (!g->fitted) return abo_fail(ABO_ERR_NOT_FITTED, "root surrogate has no posterior to broadcast");
-        if (g->p > 64) return abo_fail(ABO_ERR_INVALID, "p > 64 not supported by abo_gp_sync");
-        h[0] = (double)g->n; h[1] = (double)g->N; h[2] = (double)g->Npad; h[3] = (double)g->ldx; h[4] = g->kind;
-        h[5] = g->d; h[6] = g->p; h[7] = g->s; h[8] = g->scale; h[9] = g->noise; h[10] = (double)g->cap_pad;
-        for (int a = 0; a < g->p; ++a) h[16 + a] = g->mean_c[a];
+        int st = ABO_OK;
+        if (!g->fitted) st = ABO_ERR_NOT_FITTED;
+        else if (g->p > 64) st = ABO_ERR_INVALID;
+        h[11] = (double)st;
+        if (st == ABO_OK) {
+            h[0] = (double)g->n; h[1] = (double)g->N; h[2] = (double)g->Npad; h[3] = (double)g->ldx; h[4] = g->kind;
+            h[5] = g->d; h[6] = g->p; h[7] = g->s; h[8] = g->scale; h[9] = g->noise; h[10] = (double)g->cap_pad;
+            for (int a = 0; a < g->p; ++a) h[16 + a] = g->mean_c[a];
+        }
     }
     int rc = bcast_doubles(c, h, root);
     if (rc) return rc;
+    if ((int)h[11] != ABO_OK)
+        return abo_fail((int)h[11], (int)h[11] == ABO_ERR_NOT_FITTED ? "abo_gp_sync: the root surrogate has no posterior to broadcast"
+                                                                      : "abo_gp_sync: p > 64 is not supported");
+    // ---- receivers validate and allocate; the outcome is agreed on by all ranks before any bulk transfer
+    int mine = ABO_OK;
     if (c->rank != root) {
-        if ((int)h[5] != g->d || (int)h[6] != g->p)
-            return abo_fail(ABO_ERR_DIM, "abo_gp_sync: handle was created with d=%d p=%d, root has d=%d p=%d", g->d, g->p,
+        if ((int)h[5] != g->d || (int)h[6] != g->p) {
+            mine = abo_fail(ABO_ERR_DIM, "abo_gp_sync: handle was created with d=%d p=%d, root has d=%d p=%d", g->d, g->p,
                             (int)h[5], (int)h[6]);
-        g->kind = (int)h[4]; g->s = h[7]; g->scale = h[8]; g->noise = h[9];
-        for (int a = 0; a < g->p; ++a) g->mean_c[a] = h[16 + a];
-        const int64_t cap = (int64_t)h[10], ldx = (int64_t)h[3];
-        g->fitted = false;
-        if (cap != g->cap_pad || ldx != g->ldx || gp_shared(g)) { if ((rc = gp_alloc(g, cap, ldx))) return rc; }
-        g->n = (int64_t)h[0]; g->N = (int64_t)h[1]; g->Npad = (int64_t)h[2];
+        } else {
+            g->kind = (int)h[4]; g->s = h[7]; g->scale = h[8]; g->noise = h[9];
+            for (int a = 0; a < g->p; ++a) g->mean_c[a] = h[16 + a];
+            const int64_t cap = (int64_t)h[10], ldx = (int64_t)h[3];
+            g->fitted = false;
+            if (cap != g->cap_pad || ldx != g->ldx || gp_shared(g)) mine = gp_alloc(g, cap, ldx);
+            if (mine == ABO_OK) { g->n = (int64_t)h[0]; g->N = (int64_t)h[1]; g->Npad = (int64_t)h[2]; }
+        }
     }
-    const size_t mat = (size_t)g->cap_pad * g->cap_pad;
+    const int64_t T = g->cap_pad > 0 ? g->cap_pad / 128 : (int64_t)h[10] / 128;
+    const size_t packed = (size_t)(T * (T + 1) / 2) * 128 * 128;
+    double* stage = nullptr;
+    if (mine == ABO_OK) mine = ws_get(c, WS_KS, sizeof(double) * packed, (void**)&stage);
+    std::string my_msg = mine ? abo_last_error() : "";
+    int worst = 0, worst_rank = -1;
+    if ((rc = gather_status(c, mine, &worst, &worst_rank))) return rc;
+    if (worst != ABO_OK) {
+        if (mine) return abo_fail(mine, "%s", my_msg.c_str());
+        return abo_fail(worst, "abo_gp_sync: rank %d failed with status %d; no rank transferred anything", worst_rank, worst);
+    }
+    // ---- bulk: L and L^-1 as packed lower tiles (T(T+1)/2 of T^2: 2 x 272 MB instead of 2 x 537 MB at n = 8192),
+    //      one after the other through the same staging buffer, then the vectors
+    for (int which = 0; which < 2; ++which) {
+        double* M = which ? g->dLinv : g->dL;
+        if (c->rank == root) {
+            pack_lower_tiles_kernel<<<dim3((unsigned)T, (unsigned)T), 256, 0, c->stream>>>(M, g->ld, stage, 0);
+            KL(c);
+        }
+        NC(nccl().broadcast(stage, stage, packed, NCCL_FLOAT64, root, c->nccl_comm, c->stream));
+        if (c->rank != root) {
+            pack_lower_tiles_kernel<<<dim3((unsigned)T, (unsigned)T), 256, 0, c->stream>>>(M, g->ld, stage, 1);
+            KL(c);
+        }
+    }
     NC(nccl().groupStart());
-    NC(nccl().broadcast(g->dL, g->dL, mat, NCCL_FLOAT64, root, c->nccl_comm, c->stream));
-    NC(nccl().broadcast(g->dLinv, g->dLinv, mat, NCCL_FLOAT64, root, c->nccl_comm, c->stream));
     NC(nccl().broadcast(g->dXsT, g->dXsT, (size_t)g->ldx * g->d, NCCL_FLOAT64, root, c->nccl_comm, c->stream));
     NC(nccl().broadcast(g->dAlpha, g->dAlpha, (size_t)g->cap_pad, NCCL_FLOAT64, root, c->nccl_comm, c->stream));
     NC(nccl().broadcast(g->dBeta, g->dBeta, (size_t)g->cap_pad, NCCL_FLOAT64, root, c->nccl_comm, c->stream));
@@ -142,6 +212,13 @@ extern "C" int32_t abo_gp_sync(abo_gp* g, int32_t root) {
     NC(nccl().groupEnd());
     CU(cudaStreamSynchronize(c->stream));
     g->fitted = true;
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_ctx_ranks(const abo_ctx* c, int32_t* rank, int32_t* nranks) {
+    if (!c || !rank || !nranks) return abo_fail(ABO_ERR_INVALID, "null argument");
+    *rank = c->rank;
+    *nranks = c->nccl_comm ? c->nranks : 1;
     return ABO_OK;
 }
 

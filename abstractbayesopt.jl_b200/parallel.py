@@ -45,9 +45,25 @@ def sharded_topk(acq, surrogate, candidates, k: int, group=None):
     mine = (np.asarray(ti, dtype=np.int64) + lo, np.asarray(tv))
     if world == 1:
         return merge_topk([mine[0]], [mine[1]], k)
+    ctx = getattr(surrogate, "ctx", None)
+    if _nccl_spans(ctx, world):
+        # abo_topk_allgather: one NCCL all-gather of the (count, index, value) records + the same
+        # (value desc, index asc, NaN first) merge inside the library
+        return ctx.topk_allgather(k, mine[0], mine[1])
     gathered = [None] * world
     dist.all_gather_object(gathered, mine, group=group)
     return merge_topk([g[0] for g in gathered], [g[1] for g in gathered], k)
+
+
+def _nccl_spans(ctx, world: int) -> bool:
+    """True when `ctx` carries an NCCL communicator over exactly `world` ranks (init_nccl_context was called
+    on it).  Otherwise the torch.distributed group does the exchange (gloo in the CPU tests)."""
+    if ctx is None or not hasattr(ctx, "ranks"):
+        return False
+    try:
+        return ctx.ranks()[1] == world
+    except Exception:
+        return False
 
 
 def sharded_restarts(evaluate, logparams, group=None, nccl_ctx=None):
@@ -68,7 +84,7 @@ def sharded_restarts(evaluate, logparams, group=None, nccl_ctx=None):
     per = -(-R // world)                                   # equal-sized blocks, padded
     block = np.zeros((per, 4))
     block[:hi - lo, 0] = val; block[:hi - lo, 1:3] = np.asarray(grad).reshape(-1, 2); block[:hi - lo, 3] = info
-    if nccl_ctx is not None:
+    if _nccl_spans(nccl_ctx, world):
         allb = nccl_ctx.allgather_f64(block, world).reshape(world, per, 4)
     else:
         gathered = [None] * world

@@ -40,11 +40,9 @@ class _GpBase(AbstractSurrogate):
         self.gpx = _handle                 # posterior handle (None before update, like `gpx === nothing`)
         self._data = _data                 # (X, Yflat) host copies of the conditioning set
 
-    # -- accessors (StandardGP.jl:261-287, GradientGP.jl:842-870)
-    def _clone_unfitted(self, kernel=None, noise_var=None, mean_c=None):
-        raise NotImplementedError
 
 
+# -- accessors (StandardGP.jl:261-287, GradientGP.jl:842-870)
 def get_lengthscale(model): return [1.0 / model.kernel.inv_lengthscale]
 def get_scale(model): return [model.kernel.scale]
 def get_kernel_constructor(model): return model.kernel.constructor()

@@ -60,6 +60,9 @@ int32_t abo_ctx_create(int32_t device, abo_ctx** out);
 /* Handles of this context that are still alive are orphaned: their device memory is released and only
  * abo_gp_destroy remains valid on them (finalizers of GC'd bindings run in arbitrary order). */
 int32_t abo_ctx_destroy(abo_ctx* ctx);
+/* release everything the context caches between calls: pooled posterior buffer sets (up to 3 sets / 24 GB kept
+ * for the BO loop's per-iteration re-fit), grow-only workspaces, pinned staging memory */
+int32_t abo_ctx_trim(abo_ctx* ctx);
 int32_t abo_ctx_device(const abo_ctx* ctx, int32_t* device);
 /* cudaStream_t the context launches on (for callers that time with events on that stream) */
 int32_t abo_ctx_stream(const abo_ctx* ctx, void** stream);
@@ -160,7 +163,14 @@ int32_t abo_potrf_dev(abo_ctx* ctx, double* d_A, int64_t n, int64_t ld, int64_t*
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------------------- */
 int32_t abo_nccl_unique_id(uint8_t id[128]);
 int32_t abo_ctx_init_rank(abo_ctx* ctx, int32_t rank, int32_t nranks, const uint8_t id[128]);
-/* broadcast the posterior (X, L, L^-1, alpha, hyper-parameters) from `root` to every rank */
+/* rank / number of ranks of the context's NCCL communicator (0 / 1 when abo_ctx_init_rank was never called):
+ * callers use it to decide whether the abo_*allgather* entry points span the job */
+int32_t abo_ctx_ranks(const abo_ctx* ctx, int32_t* rank, int32_t* nranks);
+/* broadcast the posterior (X, the lower tiles of L and L^-1, alpha, hyper-parameters) from `root` to every
+ * rank.  COLLECTIVE, including its outcome: the root's state travels in the header and every rank's
+ * validation / allocation status is all-gathered before any bulk transfer, so all ranks return the same
+ * status (an un-fitted root, a handle created with another (d, p), an allocation failure) and none is left
+ * blocked inside a collective. */
 int32_t abo_gp_sync(abo_gp* gp, int32_t root);
 /* all-gather every rank's (value, global index) top-k lists and merge them with the
  * (value desc, index asc, NaN first) order; in/out arrays have length k (count valid entries) */

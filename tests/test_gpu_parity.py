@@ -443,7 +443,7 @@ def test_bo_loop_branin(abo, orc):
     gp = abo.StandardGP(1.0 * abo.with_lengthscale(abo.SqExponentialKernel(), 3.0), 1e-6)
     bo = abo.BOStruct(f, abo.ExpectedImprovement(0.01, min(y0)), gp, dom, list(X0), y0, 8, 0.0)
     bo, acq_list, _ = abo.optimize(bo, standardize="mean_scale", hyper_params=None, n_grid=4000, n_local=4, rng=rng)
-    assert len(bo.xs) == 10 + 9 and len(acq_list) == 9          # max_iter + 1 passes (bayesian_opt.jl:163-165)
+    assert len(bo.xs) == 10 + 8 and len(acq_list) == 8          # exactly max_iter passes: i += 1 precedes update(BO, ..., i) (bayesian_opt.jl:441-445, 163-165)
     assert min(float(v) for v in bo.ys_non_std) <= min(y0) + 1e-12
     assert all(a >= 0 for a in acq_list)
 
@@ -466,7 +466,7 @@ def test_bo_loop_gradient_gp(abo, orc):
     bo = abo.BOStruct(f, abo.ExpectedImprovement(0.0, best0), gp, dom, list(X0), y0, 11, 0.0)
     bo, acq_list, (mu, sd) = abo.optimize(bo, standardize="scale_only", hyper_params="all", num_restarts_HP=2,
                                          n_grid=3000, n_local=8, rng=rng)
-    assert bo.flag or len(bo.xs) == 6 + 12
+    assert bo.flag or len(bo.xs) == 6 + 11
     assert len(bo.ys_non_std) == len(bo.xs) and all(np.asarray(v).shape == (3,) for v in bo.ys_non_std)
     assert min(float(v[0]) for v in bo.ys_non_std) <= best0
     assert isinstance(bo.model, abo.GradientGP) and bo.model.gpx.n() == len(bo.xs)
