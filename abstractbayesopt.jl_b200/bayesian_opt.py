@@ -228,7 +228,9 @@ def update_bo(BO: BOStruct, x, y, i):
     BO.xs.append(np.asarray(x, dtype=np.float64).reshape(-1))
     BO.ys.append(np.asarray(y, dtype=np.float64))
     try:
-        BO.model = update_surrogate(BO.model, np.array(BO.xs), np.array(BO.ys))
+        # the lists go down as they are: a new point of the wrong dimension must surface as DimensionMismatch
+        # (test/test_bayesian_opt.jl:788-817), which — like any error but PosDef/Singular — propagates (:127-131)
+        BO.model = update_surrogate(BO.model, BO.xs, BO.ys)
     except PosDefException:
         log.info("We reached ill-conditioning, returning NON-UPDATED GP. Killing BO loop.")
         BO.model = prev

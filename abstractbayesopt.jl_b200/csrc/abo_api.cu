@@ -18,6 +18,7 @@
 #include "gemm_dmma.cuh"
 #include "kernels.cuh"
 #include "sweep_tma.cuh"
+#include "sweep_fused.cuh"
 #include "abo_internal.h"
 
 using namespace abo;
@@ -57,6 +58,9 @@ static int configure_kernels() {
     CU(cudaFuncSetAttribute(gemm_ws_kernel<KC, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
     CU(cudaFuncSetAttribute(gemm_ws_kernel<MC, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
     CU(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
+#define ABO_FS_CFG(DT) CU(cudaFuncSetAttribute(sweep_fused_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem_bytes<DT>()))
+    ABO_FS_CFG(4); ABO_FS_CFG(8); ABO_FS_CFG(12); ABO_FS_CFG(16); ABO_FS_CFG(20); ABO_FS_CFG(24); ABO_FS_CFG(32);
+#undef ABO_FS_CFG
     return ABO_OK;
 }
 
@@ -879,12 +883,65 @@ static double phi_prime0(int kind) {
     return -7.0 / 10.0;
 }
 
+// ---- fused single-kernel sweep (sweep_fused.cuh): scalar GPs up to ABO_FUSED_MAX observations --------------
+static int fused_max_n() {
+    static const int v = getenv("ABO_FUSED_MAX") ? atoi(getenv("ABO_FUSED_MAX")) : 2048;
+    return v;
+}
+static bool fused_applies(const abo_gp* g, int bo) {
+    return g->p == 1 && bo == 0 && g->d <= 32 && g->Npad <= fused_max_n();
+}
+static int sweep_fused_device(abo_gp* g, const double* dXc, int64_t m, const AcqSpec& a, double* d_mean, double* d_var,
+                              double* d_score) {
+    abo_ctx* c = g->ctx;
+    cudaStream_t st = c->stream;
+    FusedParams fp;
+    fp.spec = gp_spec(g); fp.acq = a;
+    fp.XsT = g->dXsT; fp.ldx = g->ldx; fp.n = g->n;
+    fp.T = (int)((g->n + NB - 1) / NB);
+    fp.Kld = (int)((g->n + 15) / 16 * 16);
+    fp.Xc = dXc; fp.m = m; fp.beta = g->dBeta;
+    fp.mean_out = d_mean; fp.var_out = d_var; fp.score_out = d_score;
+    fp.ntiles = (int)((m + NB - 1) / NB);
+    const int grid = std::min(c->sms, fp.ntiles);
+    int rc;
+    // private K* scratch: [CTA][2][128][Kld]; sized for the full grid so that the tensor map is stable between calls
+    if ((rc = ws_get(c, WS_KS, sizeof(double) * (size_t)c->sms * 2 * NB * fp.Kld, (void**)&fp.scratch))) return rc;
+    CUtensorMap tmA, tmB;
+    if ((rc = make_tmap_k4(&tmA, g->dLinv, g->Npad, g->Npad, g->ld))) return rc;
+    if ((rc = make_tmap_k4(&tmB, fp.scratch, fp.Kld, (int64_t)c->sms * 2 * NB, fp.Kld))) return rc;
+    if ((rc = prof_mark(c)) || (rc = prof_mark(c))) return rc;            // class 0 (K* builder): inside the fused kernel
+    if ((rc = prof_mark(c))) return rc;
+#define ABO_FS_RUN(DT) sweep_fused_kernel<DT><<<grid, FS_THREADS, fused_smem_bytes<DT>(), st>>>(tmA, tmB, fp)
+    const int d = g->d;
+    if (d <= 4) ABO_FS_RUN(4); else if (d <= 8) ABO_FS_RUN(8); else if (d <= 12) ABO_FS_RUN(12); else if (d <= 16) ABO_FS_RUN(16);
+    else if (d <= 20) ABO_FS_RUN(20); else if (d <= 24) ABO_FS_RUN(24); else ABO_FS_RUN(32);
+#undef ABO_FS_RUN
+    KL(c);
+    if ((rc = prof_mark(c))) return rc;
+    if ((rc = prof_mark(c)) || (rc = prof_mark(c))) return rc;            // class 2 (epilogue): inside the fused kernel
+    if (c->profile && c->prof_used >= 6 * 512) {
+        CU(cudaStreamSynchronize(st));
+        if ((rc = prof_collect(c))) return rc;
+    }
+    return ABO_OK;
+}
+
 // mean / var / scores for m device-resident candidates and candidate output bo; any of the
 // three outputs may be null (device pointers, length m)
 int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const double* params, double* d_mean,
                  double* d_var, double* d_score) {
     abo_ctx* c = g->ctx;
     cudaStream_t st = c->stream;
+    {
+        AcqSpec a0;
+        a0.acq = acq;
+        a0.p0 = params ? params[0] : 0.0;
+        a0.p1 = (params && acq != ACQ_UCB && acq >= 0) ? params[1] : 0.0;
+        a0.mean_c = g->mean_c[bo];
+        a0.kss = g->scale;
+        if (fused_applies(g, bo)) return sweep_fused_device(g, dXc, m, a0, d_mean, d_var, d_score);
+    }
     const int64_t Npad = g->Npad;
     const int T = (int)(Npad / NB);
     // chunk: enough tiles per launch (>= ~2048) that the persistent kernel's tail is small, K* buffer

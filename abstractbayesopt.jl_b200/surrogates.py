@@ -19,7 +19,10 @@ class AbstractSurrogate:
 def _as_points(x, d=None):
     """Vector of points -> (m, d) array.  A vector of reals is a set of 1-D points
     (src/abstract.jl:67-69, StandardGP.jl:329-347)."""
-    a = np.asarray(x, dtype=np.float64)
+    try:
+        a = np.asarray(x, dtype=np.float64)
+    except ValueError as e:                       # ragged input: points of different dimensions
+        raise DimensionMismatch(f"points do not all have the same dimension ({e})") from None
     if a.ndim == 0:
         a = a.reshape(1, 1)
     elif a.ndim == 1:
@@ -100,7 +103,10 @@ def prep_output(model, ys):
 
 
 def _flat_y(model, ys, n):
-    y = np.asarray(ys, dtype=np.float64)
+    try:
+        y = np.asarray(ys, dtype=np.float64)
+    except ValueError as e:
+        raise DimensionMismatch(f"observations do not all have the same length ({e})") from None
     if isinstance(model, GradientGP):
         if y.ndim == 1 and y.size == n * model.p:
             return np.ascontiguousarray(y)            # already prepped (out-major)
@@ -127,10 +133,8 @@ def update_surrogate(model, xs, ys, allow_append=True):
     y = _flat_y(model, ys, n)
     ctx = model.ctx or default_context()
     old = model.gpx
-    if old is not None and old.d != d:
-        raise DimensionMismatch(f"points have dimension {d}, the surrogate was conditioned on dimension {old.d}")
     pp = model.p
-    if (allow_append and old is not None and model._data is not None
+    if (allow_append and old is not None and model._data is not None and old.d == d
             and model._data[0].shape[0] == n - 1 and np.array_equal(model._data[0], X[:-1])
             and np.array_equal(model._data[1].reshape(pp, n - 1), y.reshape(pp, n)[:, :-1])):
         h = old.clone()                                  # O(1): copy-on-write handle

@@ -183,7 +183,11 @@ def test_failure_protocol(abo, orc):
     assert ei.value.info == 3
     assert abs(abo.posterior_mean(g2, [[-1.0, -1.0]])[0] - 2.0) < 1e-8      # previous model untouched
     with pytest.raises(abo.DimensionMismatch):
-        abo.update(g2, xs + [[0.0, 0.0, 0.0]], ys + [1.0]) if False else abo.posterior_mean(g2, [[0.0, 0.0, 0.0]])
+        abo.posterior_mean(g2, [[0.0, 0.0, 0.0]])                             # query of the wrong dimension
+    with pytest.raises(abo.DimensionMismatch):
+        abo.update(g2, xs + [[0.0, 0.0, 0.0]], ys + [1.0])                    # ragged xs: a 3-D point among 2-D ones
+    g3d = abo.update(g2, [[0.0, 0.0, 0.0], [1.0, 1.0, 1.0]], [1.0, 2.0])  # update() conditions the PRIOR: new data of another
+    assert g3d.gpx.d == 3 and g2.gpx.d == 2                               # dimension is a fresh posterior (StandardGP.jl:79-83)
     with pytest.raises(abo.DimensionMismatch):
         abo.update(gp, xs, ys[:1])
     # BOStruct rollback
@@ -192,6 +196,11 @@ def test_failure_protocol(abo, orc):
     bo = abo.BOStruct(f, abo.ExpectedImprovement(0.01, 2.0), g2, dom, xs, ys, 10, 0.0)
     bo = abo.update(bo, [-1.0 + 1e-12, -1.0 + 1e-12], 2.0, 0)
     assert len(bo.xs) == 2 and len(bo.ys) == 2 and bo.iter == 0 and bo.flag
+    # test/test_bayesian_opt.jl:788-817: a new point of the wrong dimension -> DimensionMismatch propagates out of update(BO, ...)
+    g3 = abo.update(abo.StandardGP(abo.SqExponentialKernel(), 0.1), xs, ys)
+    bo2 = abo.BOStruct(f, abo.ExpectedImprovement(0.01, 2.0), g3, dom, xs, ys, 10, 0.0)
+    with pytest.raises(abo.DimensionMismatch):
+        abo.update(bo2, [0.0], 0.0, 0)
 
 
 @pytest.mark.parametrize("kind", [0, 3, 5, 4])
