@@ -26,6 +26,7 @@
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <type_traits>
 
 #include "kernels.cuh"
 #include "sweep_tma.cuh"
@@ -51,6 +52,7 @@ struct FusedParams {
     double* var_out;
     double* score_out;
     int ntiles;             // candidate tiles = ceil(m / 128)
+    int dbg;                // timing experiments only (ABO_FUSED_DBG): 1 = skip the K* evaluation, 2 = skip the contraction
 };
 
 template <int DT>
@@ -62,12 +64,14 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
 // one k16 stage of the 128 x 128 product; fragment rows interleaved: warp q owns rows 8 (4 i + q) + fr
-template <bool PARTIAL>
-__device__ __forceinline__ void fused_stage(const double* __restrict__ a_s, const double* __restrict__ b_s, double (&acc)[4][8][2],
-                                            int ni) {
+// Only the row fragments ILO <= i < IHI of this warp are live (compile-time: straight-line code for every range; a
+// run-time predicate inside the unrolled loops cost as much as the DMMAs it skipped).  Partial ranges occur in the
+// last row tile of a system that is not a multiple of 128, and inside the diagonal block (rows above the diagonal).
+template <int ILO, int IHI>
+__device__ __forceinline__ void fused_stage(const double* __restrict__ a_s, const double* __restrict__ b_s, double (&acc)[4][8][2]) {
     double a[2][4], bb[2][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a[0][i] = (!PARTIAL || i < ni) ? a_s[i * 128] : 0.0;
+    for (int i = ILO; i < IHI; ++i) a[0][i] = a_s[i * 128];
 #pragma unroll
     for (int j = 0; j < 8; ++j) bb[0][j] = b_s[j * 32];
 #pragma unroll
@@ -75,18 +79,48 @@ __device__ __forceinline__ void fused_stage(const double* __restrict__ a_s, cons
         const int cur = kk & 1, nxt = cur ^ 1;
         if (kk < 3) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[nxt][i] = (!PARTIAL || i < ni) ? a_s[(kk + 1) * 512 + i * 128] : 0.0;
+            for (int i = ILO; i < IHI; ++i) a[nxt][i] = a_s[(kk + 1) * 512 + i * 128];
 #pragma unroll
             for (int j = 0; j < 8; ++j) bb[nxt][j] = b_s[(kk + 1) * 512 + j * 32];
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (!PARTIAL || i < ni) {
+        for (int i = ILO; i < IHI; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[cur][i], bb[cur][j]);
-            }
-        }
+            for (int j = 0; j < 8; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[cur][i], bb[cur][j]);
     }
+}
+__device__ __forceinline__ void fused_stage_range(const double* __restrict__ a_s, const double* __restrict__ b_s, double (&acc)[4][8][2],
+                                                  int ilo, int ihi) {
+    switch (ilo * 5 + ihi) {
+        case 0 * 5 + 4: fused_stage<0, 4>(a_s, b_s, acc); break;
+        case 0 * 5 + 3: fused_stage<0, 3>(a_s, b_s, acc); break;
+        case 0 * 5 + 2: fused_stage<0, 2>(a_s, b_s, acc); break;
+        case 0 * 5 + 1: fused_stage<0, 1>(a_s, b_s, acc); break;
+        case 1 * 5 + 4: fused_stage<1, 4>(a_s, b_s, acc); break;
+        case 1 * 5 + 3: fused_stage<1, 3>(a_s, b_s, acc); break;
+        case 1 * 5 + 2: fused_stage<1, 2>(a_s, b_s, acc); break;
+        case 2 * 5 + 4: fused_stage<2, 4>(a_s, b_s, acc); break;
+        case 2 * 5 + 3: fused_stage<2, 3>(a_s, b_s, acc); break;
+        case 3 * 5 + 4: fused_stage<3, 4>(a_s, b_s, acc); break;
+        default: break;                                              // empty range
+    }
+}
+
+// kernel profile value by FAMILY (0: SE, 1: Matern-5/2 kinds, 2: Matern-7/2 kinds): the family switch is taken once per
+// candidate tile, not once per entry (ncu: the per-entry dispatch branches and their re-convergence were ~15 % of the
+// builder's issue slots, plus instruction-cache misses on three inlined copies of the profile code)
+template <int FAM>
+__device__ __forceinline__ double phi_value(int kind, double u) {
+    if (FAM == 0) return exp(-u / 2);
+    const double r = sqrt(u);
+    if (FAM == 1) {
+        const double q5 = 2.23606797749978969641;
+        const double v = (1 + q5 * r + u * (5.0 / 3.0)) * exp(-q5 * r);          // 5 u / 3 without the FP64 division (1 ulp of one term)
+        return (kind == K_AM52 && u < 1e-10) ? 1.0 - (5.0 / 6.0) * u : v;
+    }
+    const double q7 = 2.64575131106459059050;
+    const double v = (1 + q7 * r + u * (14.0 / 5.0) + (7.0 / 15.0) * q7 * r * u) * exp(-q7 * r);
+    return (kind == K_AM72 && u < 1e-10) ? 1.0 - (7.0 / 10.0) * u : v;
 }
 
 template <int DT>
@@ -158,6 +192,10 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int e = tid; e < 2 * 128 * padw; e += 256) my_scratch[(size_t)(e / padw) * p.Kld + n + (e % padw)] = 0.0;
     }
 
+    // K* tile of candidate tile j -> scratch slot j & 1.  Work items of (32 training points) x (32 candidates), lane = point
+    // (coalesced 256-byte stores along k); BCU candidates in flight per lane: with two warps per scheduler that is 2 x BCU
+    // independent FP64 chains, enough to cover the DADD -> DFMA latency (4 left the FP64 pipe ~50 % idle, ncu stall_wait).
+    constexpr int BCU = 8;
     auto build = [&](int j) {
         const int64_t c_base = ((int64_t)b + (int64_t)j * G) * 128;
         double* tile = my_scratch + (size_t)(j & 1) * 128 * p.Kld;
@@ -167,31 +205,55 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             sc[e] = (k < d && gc < p.m) ? p.spec.s * p.Xc[gc * d + k] : 0.0;
         }
         bar_consumers();
-        const int nitems = (int)((n + 31) / 32) * 4;                  // (32 training points) x (32 candidates)
-        for (int item = warp; item < nitems; item += 8) {
-            const int64_t i = (int64_t)(item >> 2) * 32 + lane;
-            const int c0 = (item & 3) * 32;
-            const bool live = i < n;
-            double x[DT];
+        const int nitems = ((p.dbg & 1) && j > 1) ? 0 : (int)((n + 31) / 32) * 4;
+        auto items = [&](auto fam_tag) {
+            constexpr int FAM = decltype(fam_tag)::value;
+            constexpr bool PREF = DT <= 12;                           // next item's coordinates loaded one item ahead (register budget)
+            double xn[PREF ? DT : 1];
+            if (PREF) {
+                const int64_t i0 = (int64_t)(warp >> 2) * 32 + lane;
 #pragma unroll
-            for (int k = 0; k < DT; ++k) x[k] = (k < d && live) ? p.XsT[(int64_t)k * p.ldx + i] : 0.0;
-            double* col = tile + i;
-#pragma unroll 1
-            for (int c = c0; c < c0 + 32; c += 4) {
-                double u[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int k = 0; k < DT; ++k) xn[PREF ? k : 0] = (k < d && i0 < n && warp < nitems) ? p.XsT[(int64_t)k * p.ldx + i0] : 0.0;
+            }
+            for (int item = warp; item < nitems; item += 8) {
+                const int64_t i = (int64_t)(item >> 2) * 32 + lane;
+                const int c0 = (item & 3) * 32;
+                const bool live = i < n;
+                double x[DT];
+                if (PREF) {
 #pragma unroll
-                for (int k = 0; k < DT; ++k) {
+                    for (int k = 0; k < DT; ++k) x[k] = xn[PREF ? k : 0];
+                    const int64_t i2 = (int64_t)((item + 8) >> 2) * 32 + lane;
+                    const bool nxt = (item + 8 < nitems) && i2 < n;
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) { const double df = x[k] - sc[(c + r) * DT + k]; u[r] = fma(df, df, u[r]); }
+                    for (int k = 0; k < DT; ++k) xn[PREF ? k : 0] = (k < d && nxt) ? p.XsT[(int64_t)k * p.ldx + i2] : 0.0;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < DT; ++k) x[k] = (k < d && live) ? p.XsT[(int64_t)k * p.ldx + i] : 0.0;
                 }
+                double* col = tile + i;
+#pragma unroll 1
+                for (int c = c0; c < c0 + 32; c += BCU) {
+                    double u[BCU];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    double ph, dph, ddph;
-                    phi_eval(p.spec.kind, u[r], ph, dph, ddph);
-                    if (live) col[(size_t)(c + r) * p.Kld] = p.spec.scale * ph;
+                    for (int r = 0; r < BCU; ++r) u[r] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DT; ++k) {
+#pragma unroll
+                        for (int r = 0; r < BCU; ++r) { const double df = x[k] - sc[(c + r) * DT + k]; u[r] = fma(df, df, u[r]); }
+                    }
+#pragma unroll
+                    for (int r = 0; r < BCU; ++r) {
+                        const double v = p.spec.scale * phi_value<FAM>(p.spec.kind, u[r]);
+                        if (live) col[(size_t)(c + r) * p.Kld] = v;
+                    }
                 }
             }
-        }
+        };
+        const int kind = p.spec.kind;
+        if (kind == K_SE) items(std::integral_constant<int, 0>{});
+        else if (kind == K_M52 || kind == K_AM52 || kind == K_ADM52) items(std::integral_constant<int, 1>{});
+        else items(std::integral_constant<int, 2>{});
         fence_proxy_async_global();                                   // generic-proxy stores before the TMA (async-proxy) reads
         __threadfence();
         bar_consumers();
@@ -200,9 +262,9 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     int stage = 0;
     uint32_t phase = 0;
-    if (ntl > 0) build(0);
-    for (int j = 0; j < ntl; ++j) {
-        if (j + 1 < ntl) build(j + 1);
+    for (int j = -1; j < ntl; ++j) {
+        if (j + 1 < ntl) build(j + 1);                                // one tile ahead of the contraction (single call site: one copy of the code)
+        if (j < 0) continue;
         const int64_t c_base = ((int64_t)b + (int64_t)j * G) * 128;
         for (int ib = 0; ib < p.T; ++ib) {
             const int nk = min((ib + 1) * 8, nk_max);
@@ -217,24 +279,27 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 for (int jj = 0; jj < 8; ++jj) { acc[i][jj][0] = 0.0; acc[i][jj][1] = 0.0; }
             const int a_off = ((8 * q + fr) << 2) + fk;
             const int b_off = SW_OPER_DOUBLES + ((wn + fr) << 2) + fk;
-            if (rows == 128) {
-                for (int kt = 0; kt < nk; ++kt) {
-                    mbar_wait(&full[stage], phase);
-                    const double* st = stage_base + (size_t)stage * (2 * SW_OPER_DOUBLES);
-                    fused_stage<false>(st + a_off, st + b_off, acc, 4);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[stage]);
-                    if (++stage == FS_STAGES) { stage = 0; phase ^= 1; }
-                }
-            } else {
-                for (int kt = 0; kt < nk; ++kt) {
-                    mbar_wait(&full[stage], phase);
-                    const double* st = stage_base + (size_t)stage * (2 * SW_OPER_DOUBLES);
-                    fused_stage<true>(st + a_off, st + b_off, acc, ni);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[stage]);
-                    if (++stage == FS_STAGES) { stage = 0; phase ^= 1; }
-                }
+            // k16 steps left of the diagonal block: every live row fragment; inside the diagonal block (k0 = m0 + 16 t) only the
+            // rows >= k0 are non-zero in L^-1: fragments f >= 2 t, i.e. i >= ceil((2 t - q) / 4) for this warp — the
+            // upper-triangle half of the diagonal tile is never multiplied (it is (T + 1) / T of the work at T row tiles)
+            const int nk_full = (rows == 128 && !(p.dbg & 2)) ? min(nk, ib * 8) : 0;
+            for (int kt = 0; kt < nk_full; ++kt) {
+                mbar_wait(&full[stage], phase);
+                const double* st = stage_base + (size_t)stage * (2 * SW_OPER_DOUBLES);
+                fused_stage<0, 4>(st + a_off, st + b_off, acc);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+                if (++stage == FS_STAGES) { stage = 0; phase ^= 1; }
+            }
+            for (int kt = nk_full; kt < nk; ++kt) {
+                mbar_wait(&full[stage], phase);
+                const double* st = stage_base + (size_t)stage * (2 * SW_OPER_DOUBLES);
+                const int t = kt - ib * 8;                            // < 0 left of the diagonal block
+                const int ilo = t > 0 ? max(0, (2 * t - q + 3) >> 2) : 0;
+                if (!(p.dbg & 2)) fused_stage_range(st + a_off, st + b_off, acc, ilo, ni);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+                if (++stage == FS_STAGES) { stage = 0; phase ^= 1; }
             }
             // ---- tile epilogue: column sums of W^2 and of W * beta over the tile's rows
             double bt[4];
