@@ -19,7 +19,7 @@ SYMBOLS = [
     "abo_ctx_launch_count", "abo_ctx_profile", "abo_ctx_profile_read", "abo_debug_potf2_clocks", "abo_gp_create", "abo_gp_destroy", "abo_gp_set_params", "abo_gp_fit", "abo_gp_append",
     "abo_gp_clone", "abo_gp_n", "abo_gp_alpha", "abo_gp_factor", "abo_gp_posterior", "abo_gp_posterior_cov", "abo_acq_eval", "abo_acq_eval_dev", "abo_acq_eval_grad",
     "abo_nlml_batch", "abo_potrf_dev", "abo_fill_distance", "abo_nccl_unique_id", "abo_ctx_init_rank", "abo_gp_sync",
-    "abo_topk_allgather", "abo_allgather_f64", "abo_ctx_ranks", "abo_ctx_trim",
+    "abo_topk_allgather", "abo_allgather_f64", "abo_ctx_ranks", "abo_ctx_trim", "abo_acq_eval_multi",
 ]
 
 
@@ -78,6 +78,7 @@ def lib():
             "abo_gp_posterior_cov": [vp, vp, i64, i32, vp],
             "abo_acq_eval": [vp, i32, vp, vp, i64, vp, i64, vp, vp],
             "abo_acq_eval_dev": [vp, i32, vp, vp, i64, vp, i64, vp, vp],
+            "abo_acq_eval_multi": [vp, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp],
             "abo_acq_eval_grad": [vp, i32, vp, vp, i64, vp, vp, vp, vp],
             "abo_nlml_batch": [vp, vp, vp, i64, vp, i64, vp, vp, vp],
             "abo_potrf_dev": [vp, vp, i64, i64, C.POINTER(i64)],
@@ -314,6 +315,22 @@ class GpHandle:
         k = min(int(k), m)
         ti = np.empty(max(k, 1), dtype=np.int64); tv = np.empty(max(k, 1))
         check(lib().abo_acq_eval(self._h, acq_id, ptr(params), ptr(Xc), m, ptr(scores), k, ptr(ti), ptr(tv)))
+        return scores, ti[:k], tv[:k]
+
+    def acq_eval_multi(self, acq_ids, weights, params, Xc, k=0, want_scores=True):
+        """Weighted sum of acquisition members (EI / PI / UCB / GradientNormUCB = 3) from one posterior pass."""
+        Xc = f64(Xc)
+        if Xc.ndim != 2 or Xc.shape[1] != self.d:
+            raise DimensionMismatch(f"query points must be m x {self.d}")
+        m = Xc.shape[0]
+        ids = np.ascontiguousarray(acq_ids, dtype=np.int32); w = f64(weights)
+        pr = np.zeros((len(ids), 2)); 
+        for q, row in enumerate(params):
+            pr[q, :len(row)] = row
+        scores = np.empty(m) if want_scores else None
+        k = min(int(k), m)
+        ti = np.empty(max(k, 1), dtype=np.int64); tv = np.empty(max(k, 1))
+        check(lib().abo_acq_eval_multi(self._h, len(ids), ptr(ids), ptr(w), ptr(pr), ptr(Xc), m, ptr(scores), k, ptr(ti), ptr(tv)))
         return scores, ti[:k], tv[:k]
 
     def acq_eval_grad(self, acq_id, params, Xc):

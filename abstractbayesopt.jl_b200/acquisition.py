@@ -73,51 +73,57 @@ class UpperConfidenceBound(AbstractAcquisition):
     def update(self, ys, surrogate): return self
 
 
+ACQ_GRADNORM_UCB = 3
+
+
+def _fd_value_and_grad(acq, surrogate, x, rel_step=6.0554544523933395e-06):
+    """Value and central-difference gradient for a batch of points in ONE batched evaluation of m (2 d + 1) points
+    (what Optim's finite-difference default does one point and one coordinate at a time, acq_utils.jl:55-63);
+    step = cbrt(eps) * max(1, |x_k|)."""
+    X = np.asarray(x, dtype=np.float64)
+    m, d = X.shape
+    h = rel_step * np.maximum(1.0, np.abs(X))
+    P = np.repeat(X[:, None, :], 2 * d + 1, axis=1)
+    for k in range(d):
+        P[:, 1 + 2 * k, k] += h[:, k]; P[:, 2 + 2 * k, k] -= h[:, k]
+    v = np.asarray(acq(surrogate, P.reshape(-1, d))).reshape(m, 2 * d + 1)
+    grad = (v[:, 1::2] - v[:, 2::2]) / (2 * h)
+    return v[:, 0].copy(), grad
+
+
 @dataclass(frozen=True)
 class GradientNormUCB(AbstractAcquisition):
-    """GradientNormUCB(β) (gradNormUCB.jl:12-51): UCB on the squared 2-norm of the gradient of a
-    GradientGP.  Per point: m = posterior gradient mean, Σ = posterior gradient covariance (p-1 x p-1),
-    -(m·m + tr Σ) + β sqrt(max(4 mᵀΣm + 2‖Σ‖_F², 1e-12)).  Means and the p x p covariance blocks come
-    from batched device calls (abo_gp_posterior / abo_gp_posterior_cov), chunked so that
-    points*p <= 4096; there is no fused sweep for this one."""
+    """GradientNormUCB(β) (gradNormUCB.jl:12-51): UCB on the squared 2-norm of the gradient of a GradientGP.  Per point:
+    m = posterior gradient mean, Σ = posterior gradient covariance (d x d), -(m·m + tr Σ) + β sqrt(max(4 mᵀΣm + 2‖Σ‖_F², 1e-12)).
+    Evaluated on the device for the whole candidate set (abo_acq_eval_multi: K* with all p output columns, one DMMA
+    triangular product, the p x p covariance blocks and the formula in the epilogue kernels)."""
     beta: float
+    acq_id = ACQ_GRADNORM_UCB
 
     def params(self): return [self.beta]
     def copy(self): return GradientNormUCB(self.beta)
     def update(self, ys, surrogate): return self
 
-    def __call__(self, surrogate, x):
+    def _eval(self, surrogate, x, k=0, want_scores=True):
         h = _need_posterior(surrogate)
-        X = _as_points(x, h.d)
-        p = h.p
-        if p < 2:
+        if h.p < 2:
             raise TypeError("GradientNormUCB needs a GradientGP surrogate")
-        out = np.empty(len(X))
-        step = max(1, 4096 // p)
-        for c0 in range(0, len(X), step):
-            Xc = X[c0:c0 + step]
-            mc = len(Xc)
-            mean, _ = h.posterior(Xc, p, True, False)
-            cov = h.posterior_cov(Xc, p)
-            mean = mean.reshape(p, mc)
-            for c in range(mc):
-                idx = np.arange(1, p) * mc + c
-                m = mean[1:, c]
-                S = cov[np.ix_(idx, idx)]
-                mu_sq = float(m @ m + np.trace(S))
-                var_sq = float(4.0 * m @ (S @ m) + 2.0 * np.sum(S * S))
-                out[c0 + c] = -mu_sq + self.beta * np.sqrt(max(var_sq, 1e-12))
-        return out
+        return h.acq_eval_multi([ACQ_GRADNORM_UCB], [1.0], [[self.beta, 0.0]], _as_points(x, h.d), k=k, want_scores=want_scores)
+
+    def __call__(self, surrogate, x):
+        return self._eval(surrogate, x)[0]
 
     def topk(self, surrogate, x, k, want_scores=True):
-        s = self(surrogate, x)
-        ti, tv = merge_topk([np.arange(len(s))], [s], k)
-        return s, ti, tv
+        return self._eval(surrogate, x, k=k, want_scores=want_scores)
+
+    def value_and_grad(self, surrogate, x):
+        return _fd_value_and_grad(self, surrogate, _as_points(x, _need_posterior(surrogate).d))
 
 
 class EnsembleAcquisition(AbstractAcquisition):
-    """EnsembleAcquisition(weights, acquisitions) (EnsembleAcq.jl:12-55): non-negative weights,
-    normalised to sum 1; value = Σ w_i acq_i(surrogate, x)."""
+    """EnsembleAcquisition(weights, acquisitions) (EnsembleAcq.jl:12-55): non-negative weights, normalised to sum 1;
+    value = Σ w_i acq_i(surrogate, x).  When every member is EI / PI / UCB / GradientNormUCB the members share ONE
+    posterior pass on the device (abo_acq_eval_multi); other members are evaluated one after the other."""
 
     def __init__(self, weights, acquisitions):
         w = np.asarray(weights, dtype=np.float64)
@@ -133,10 +139,24 @@ class EnsembleAcquisition(AbstractAcquisition):
     def copy(self): return EnsembleAcquisition(self.weights.copy(), [a.copy() for a in self.acquisitions])
     def update(self, ys, surrogate): return EnsembleAcquisition(self.weights, [a.update(ys, surrogate) for a in self.acquisitions])
 
-    def __call__(self, surrogate, x):
-        return sum(w * a(surrogate, x) for w, a in zip(self.weights, self.acquisitions))
+    def _fusable(self):
+        return len(self.acquisitions) <= 8 and all(getattr(a, "acq_id", -1) in (0, 1, 2, 3) and not isinstance(a, EnsembleAcquisition)
+                                                   for a in self.acquisitions)
 
-    def topk(self, surrogate, x, k, want_scores=True):
-        s = self(surrogate, x)
+    def _eval(self, surrogate, x, k=0, want_scores=True):
+        h = _need_posterior(surrogate)
+        if self._fusable():
+            return h.acq_eval_multi([a.acq_id for a in self.acquisitions], self.weights, [a.params() for a in self.acquisitions],
+                                    _as_points(x, h.d), k=k, want_scores=want_scores)
+        s = sum(w * a(surrogate, x) for w, a in zip(self.weights, self.acquisitions))
         ti, tv = merge_topk([np.arange(len(s))], [s], k)
         return s, ti, tv
+
+    def __call__(self, surrogate, x):
+        return self._eval(surrogate, x)[0]
+
+    def topk(self, surrogate, x, k, want_scores=True):
+        return self._eval(surrogate, x, k=k, want_scores=want_scores)
+
+    def value_and_grad(self, surrogate, x):
+        return _fd_value_and_grad(self, surrogate, _as_points(x, _need_posterior(surrogate).d))

@@ -56,8 +56,9 @@ def optimize_acquisition(acqf, surrogate, domain, n_grid=10_000, n_local=100, rn
     returns the stable top-n_local (replaces acqf(...) + sortperm, :50-52) → box-constrained L-BFGS
     refinement from those starts.  The reference refines the starts one after the other with
     finite-difference gradients of single-point evaluations (:55-63); here all starts advance in
-    lock-step and every step is ONE batched call returning the acquisition and its analytic
-    gradient for all of them (refine=True).  refine="scipy" keeps the reference's sequential,
+    lock-step and every step is ONE batched call returning the acquisition and its gradient for all of
+    them (refine=True): analytic for EI / PI / UCB (abo_acq_eval_grad), batched central differences —
+    all starts x (2 d + 1) points in one device call — for GradientNormUCB and ensembles.  refine="scipy" keeps the reference's sequential,
     finite-difference scheme (SciPy L-BFGS-B); refine=False returns the best grid point."""
     rng = np.random.default_rng() if rng is None else rng
     grid = latin_hypercube(n_grid, domain.lower, domain.upper, rng)
@@ -65,8 +66,6 @@ def optimize_acquisition(acqf, surrogate, domain, n_grid=10_000, n_local=100, rn
     starts = grid[top_idx]
     if refine is False or len(starts) == 0:
         return np.array(starts[0])
-    if refine is True and getattr(acqf, "acq_id", -1) < 0:
-        refine = "scipy"                                # no fused value+gradient path (GradientNormUCB, ensembles)
     if refine == "scipy":
         best_acq, best_x = -math.inf, None
         bounds = list(zip(domain.lower, domain.upper))

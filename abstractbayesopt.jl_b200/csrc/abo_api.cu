@@ -1199,14 +1199,20 @@ static void topk_emit(std::vector<TopItem>& items, int64_t k, int64_t* top_idx, 
     for (int64_t i = 0; i < cnt; ++i) { top_idx[i] = items[(size_t)i].idx; top_val[i] = items[(size_t)i].val; }
 }
 
+static int scores_select_readback(abo_ctx* c, const double* dS, int64_t m, double* h_scores, int64_t k, int64_t* top_idx, double* top_val);
 static int acq_eval_common(abo_gp* g, int acq_id, const double* params, const double* dXc, int64_t m, double* d_scores,
                            double* h_scores, int64_t k, int64_t* top_idx, double* top_val) {
     abo_ctx* c = g->ctx;
-    cudaStream_t st = c->stream;
     int rc;
     double* dS = d_scores;
     if (!dS && (rc = ws_get(c, WS_OUT_A, sizeof(double) * (size_t)m, (void**)&dS))) return rc;
     if ((rc = sweep_device(g, dXc, m, 0, acq_id, params, nullptr, nullptr, dS))) return rc;
+    return scores_select_readback(c, dS, m, h_scores, k, top_idx, top_val);
+}
+// scores on the device -> (optionally) the host, and the stable top-k of them
+static int scores_select_readback(abo_ctx* c, const double* dS, int64_t m, double* h_scores, int64_t k, int64_t* top_idx, double* top_val) {
+    cudaStream_t st = c->stream;
+    int rc;
     const int64_t K = std::min(k, m);
     if (K > 0 && m <= SEL_MIN_M) {
         // small sets (the 10 000-point grid of optimize_acquisition): the 19 selection launches would cost more than
@@ -1397,3 +1403,4 @@ extern "C" int32_t abo_potrf_dev(abo_ctx* c, double* d_A, int64_t n, int64_t ld,
 }
 
 #include "abo_extra.cuh"
+#include "abo_multi.cuh"

@@ -49,8 +49,8 @@ typedef enum {
 } abo_kernel;
 
 /* acquisition functions (src/acquisition_functions/{ExpectedImprovement,ProbabilityImprovement,
- * UpperConfidenceBound}.jl).  params: EI/PI = {xi, best_y}; UCB = {beta}. */
-typedef enum { ABO_ACQ_EI = 0, ABO_ACQ_PI = 1, ABO_ACQ_UCB = 2 } abo_acq;
+ * UpperConfidenceBound,gradNormUCB}.jl).  params: EI/PI = {xi, best_y}; UCB / GradientNormUCB = {beta}. */
+typedef enum { ABO_ACQ_EI = 0, ABO_ACQ_PI = 1, ABO_ACQ_UCB = 2, ABO_ACQ_GRADNORM_UCB = 3 /* abo_acq_eval_multi only */ } abo_acq;
 
 int32_t abo_version(void);
 const char* abo_last_error(void);          /* thread-local message of the last failure */
@@ -134,6 +134,16 @@ int32_t abo_acq_eval(abo_gp* gp, int32_t acq_id, const double* params, const dou
  * m doubles) may be NULL.  top_idx/top_val are host buffers. */
 int32_t abo_acq_eval_dev(abo_gp* gp, int32_t acq_id, const double* params, const double* d_Xc,
                          int64_t m, double* d_scores, int64_t k, int64_t* top_idx, double* top_val);
+
+/* EnsembleAcquisition (src/acquisition_functions/EnsembleAcq.jl:53-55): scores = sum_q weights[q] * acq_q(surrogate, Xc) with
+ * members acq_ids[q] in {ABO_ACQ_EI, ABO_ACQ_PI, ABO_ACQ_UCB, ABO_ACQ_GRADNORM_UCB}; params is nmem x 2 (row q = the member's
+ * {xi, best_y} or {beta, unused}); weights are used as given (the reference normalises them in the constructor).  ONE
+ * posterior pass serves all members.  GradientNormUCB (gradNormUCB.jl:43-51, needs a GradientGP): per candidate the
+ * posterior gradient mean m and the d x d posterior gradient covariance S are formed on the device —
+ * -(m.m + tr S) + beta sqrt(max(4 m^T S m + 2 |S|_F^2, 1e-12)) — a single member with weight 1 is the plain acquisition.
+ * scores / top-k as abo_acq_eval. */
+int32_t abo_acq_eval_multi(abo_gp* gp, int32_t nmem, const int32_t* acq_ids, const double* weights, const double* params,
+                           const double* Xc, int64_t m, double* scores, int64_t k, int64_t* top_idx, double* top_val);
 
 /* acquisition value AND its gradient with respect to the query point for a batch of m points
  * (batched local refinement of optimize_acquisition, acq_utils.jl:55-71: the reference differentiates

@@ -9,8 +9,10 @@ module AboCuda
 using LinearAlgebra
 import AbstractGPs, ForwardDiff
 using ..AbstractBayesOpt: AbstractSurrogate, AbstractAcquisition, ExpectedImprovement,
-    ProbabilityImprovement, UpperConfidenceBound, StandardGP, extract_scale_and_lengthscale
-import ..AbstractBayesOpt: update, posterior_mean, posterior_var, nlml, nlml_ls, prep_input, prep_output,
+    ProbabilityImprovement, UpperConfidenceBound, GradientNormUCB, EnsembleAcquisition, StandardGP, GradientGP,
+    extract_scale_and_lengthscale
+import ..AbstractBayesOpt: update, posterior_mean, posterior_var, posterior_grad_mean, posterior_grad_var,
+    posterior_grad_cov, unstandardized_mean_and_var, nlml, nlml_ls, prep_input, prep_output,
     get_lengthscale, get_scale, get_kernel_constructor, _get_minimum, _update_model_parameters,
     get_mean_std, std_y, rescale_model
 
@@ -176,5 +178,183 @@ function nlml(m::CuStandardGP, p::AbstractVector{D}, xs, ys) where {T,V,N,D<:For
     ForwardDiff.Dual{T}(v, parts)
 end
 nlml_ls(m::CuStandardGP, log_ℓ, log_scale::Float64, xs, ys) = nlml(m, [log_ℓ, oftype(log_ℓ, log_scale)], xs, ys)
+
+
+# unstandardized_mean_and_var(::StandardGP, xs, params) (StandardGP.jl:395-404; tutorials 2D_BO.jl:177): mean and variance
+# from ONE sweep instead of mean_and_var on a FiniteGP
+function unstandardized_mean_and_var(m::CuStandardGP, xs::AbstractVector, params)
+    μ, σ = params
+    mn, v = posterior(m, xs, true, true)
+    (mn .* σ) .+ μ, v .* (σ^2)
+end
+
+# =====================================================================================================================
+# CuGradientGP — GPU twin of GradientGP (src/surrogates/GradientGP.jl:17-22): value + gradient observations, the
+# N = n (d + 1) system with the derivative blocks of gradKernel (:573-606) built, factorised and queried on the device.
+# Observations cross the ABI OUT-MAJOR, exactly prep_output (:919-922); multi-output results come back out-major.
+# =====================================================================================================================
+struct CuGradientGP{T} <: AbstractSurrogate
+    prior::GradientGP{T}
+    gpx::Union{Nothing,Handle}
+    X::Union{Nothing,Matrix{Float64}}   # d x n conditioning points held by the handle
+    y::Union{Nothing,Vector{Float64}}   # out-major observations (length n p)
+end
+CuGradientGP(prior::GradientGP, gpx) = CuGradientGP(prior, gpx, nothing, nothing)
+CuGradientGP(kernel, p::Int, noise_var; kw...) = CuGradientGP(GradientGP(kernel, p, noise_var; kw...), nothing)
+
+get_lengthscale(m::CuGradientGP) = get_lengthscale(m.prior)
+get_scale(m::CuGradientGP) = get_scale(m.prior)
+get_kernel_constructor(m::CuGradientGP) = get_kernel_constructor(m.prior)
+prep_input(m::CuGradientGP, xs) = xs                                   # the device builds the multi-output layout itself
+prep_output(m::CuGradientGP, ys::Vector) = prep_output(m.prior, ys)    # vec(permutedims(hcat(ys...))): out-major
+_get_minimum(m::CuGradientGP, ys) = _get_minimum(m.prior, ys)
+get_mean_std(m::CuGradientGP, ys, choice) = get_mean_std(m.prior, ys, choice)
+std_y(m::CuGradientGP, ys, μ, σ) = std_y(m.prior, ys, μ, σ)
+rescale_model(m::CuGradientGP, σ) = CuGradientGP(rescale_model(m.prior, σ), nothing)
+_update_model_parameters(m::CuGradientGP, k) = CuGradientGP(_update_model_parameters(m.prior, k), nothing)
+
+kernel_id(m::CuGradientGP) = KERNEL_IDS[nameof(typeof(get_kernel_constructor(m)))]
+inv_lengthscale(m::CuGradientGP) = m.prior.gp.kernel.base_kernel.kernel.transform.s[1]   # stored s (GradientGP.jl:842)
+# gradConstMean's constructor returns a CustomMean closing over c (GradientGP.jl:505-515): evaluate it per output
+mean_consts(m::CuGradientGP, x1) = Float64[AbstractGPs.mean_vector(m.prior.gp.mean, [(x1, o)])[1] for o in 1:m.prior.p]
+
+function Base.copy(m::CuGradientGP)                                    # GradientGP.jl:32
+    m.gpx === nothing && return CuGradientGP(m.prior, nothing)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:abo_gp_clone, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), m.gpx.h, r))
+    CuGradientGP(m.prior, Handle(r[]), m.X, m.y)
+end
+
+function update(m::CuGradientGP, xs::AbstractVector, ys::AbstractVector)   # GradientGP.jl:659-668
+    X = Matrix{Float64}(points(collect(xs))); d, n = size(X); p = m.prior.p
+    p == d + 1 || throw(DimensionMismatch("GradientGP: p must equal d + 1"))
+    (length(ys) == n && all(length(y) == p for y in ys)) || throw(DimensionMismatch("ys must hold n vectors of length p"))
+    y = collect(Float64, vec(permutedims(reduce(hcat, ys))))           # out-major: [f(x1..xn); d1 f(x1..xn); ...]
+    # one more point on top of what the handle holds: block append of its p rows, O(N^2 p), on a copy-on-write clone
+    if m.gpx !== nothing && m.X !== nothing && size(m.X) == (d, n - 1) && view(X, :, 1:n-1) == m.X &&
+       reshape(y, n, p)[1:n-1, :] == reshape(m.y, n - 1, p)
+        c = copy(m); info = Ref{Int64}(0)
+        xn = X[:, n]; yn = collect(Float64, ys[n])
+        rc = GC.@preserve xn yn ccall((:abo_gp_append, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}),
+            c.gpx.h, xn, yn, info)
+        check(rc, info[])
+        return CuGradientGP(m.prior, c.gpx, X, y)
+    end
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:abo_gp_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}),
+        ctx().h, kernel_id(m), d, p, r))
+    h = Handle(r[])
+    mc = mean_consts(m, X[:, 1])
+    check(ccall((:abo_gp_set_params, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, Ptr{Float64}),
+        h.h, inv_lengthscale(m), get_scale(m)[1], m.prior.noise_var, mc))
+    info = Ref{Int64}(0)
+    rc = GC.@preserve X y ccall((:abo_gp_fit, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ref{Int64}),
+        h.h, X, y, n, info)
+    check(rc, info[])
+    CuGradientGP(m.prior, h, X, y)
+end
+
+# outputs = 1: value only (posterior_mean / posterior_var, GradientGP.jl:985-1003); outputs = p: all outputs, out-major
+function posterior(m::CuGradientGP, x::AbstractVector, outputs::Integer, want_mean::Bool, want_var::Bool)
+    Xc = Matrix{Float64}(points(collect(x))); mcount = size(Xc, 2)
+    μ = want_mean ? Vector{Float64}(undef, mcount * outputs) : Float64[]
+    v = want_var ? Vector{Float64}(undef, mcount * outputs) : Float64[]
+    check(GC.@preserve Xc μ v ccall((:abo_gp_posterior, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Float64}, Ptr{Float64}),
+        m.gpx.h, Xc, mcount, outputs, want_mean ? pointer(μ) : C_NULL, want_var ? pointer(v) : C_NULL))
+    μ, v
+end
+posterior_mean(m::CuGradientGP, x::AbstractVector) = posterior(m, x, 1, true, false)[1]
+posterior_var(m::CuGradientGP, x::AbstractVector) = posterior(m, x, 1, false, true)[2]
+posterior_mean(m::CuGradientGP, x::Real) = posterior_mean(m, [x])
+posterior_var(m::CuGradientGP, x::Real) = posterior_var(m, [x])
+posterior_grad_mean(m::CuGradientGP, x) = posterior(m, x, m.prior.p, true, false)[1]     # GradientGP.jl:936-939
+posterior_grad_var(m::CuGradientGP, x) = posterior(m, x, m.prior.p, false, true)[2]      # GradientGP.jl:952-955
+function posterior_grad_cov(m::CuGradientGP, x)                                          # GradientGP.jl:968-971
+    Xc = Matrix{Float64}(points(collect(x))); mcount = size(Xc, 2); M = mcount * m.prior.p
+    cov = Matrix{Float64}(undef, M, M)
+    check(GC.@preserve Xc cov ccall((:abo_gp_posterior_cov, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Float64}), m.gpx.h, Xc, mcount, m.prior.p, cov))
+    cov                                                                # symmetric: row- vs column-major is immaterial
+end
+
+function unstandardized_mean_and_var(m::CuGradientGP, X, params::Tuple)                  # GradientGP.jl:1019-1030
+    μ, σ = params[1], params[2][1]
+    mn, v = posterior(m, X, m.prior.p, true, true)
+    (reshape(mn, :, m.prior.p) .* σ) .+ μ', reshape(v, :, m.prior.p) .* (σ^2)
+end
+
+# value-output acquisitions on a GradientGP: the same fused sweep (K* has value and derivative rows, value column only)
+function acq_eval(a::AbstractAcquisition, m::CuGradientGP, x::AbstractVector; k::Integer=0)
+    Xc = Matrix{Float64}(points(collect(x))); mcount = size(Xc, 2)
+    scores = Vector{Float64}(undef, mcount); p = acq_params(a)
+    ti = Vector{Int64}(undef, max(k, 1)); tv = Vector{Float64}(undef, max(k, 1))
+    check(GC.@preserve Xc scores p ti tv ccall((:abo_acq_eval, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Float64}),
+        m.gpx.h, acq_id(a), p, Xc, mcount, scores, min(k, mcount), ti, tv))
+    scores, ti[1:min(k, mcount)] .+ 1, tv[1:min(k, mcount)]
+end
+(a::ExpectedImprovement)(m::CuGradientGP, x::AbstractVector) = acq_eval(a, m, x)[1]
+(a::ProbabilityImprovement)(m::CuGradientGP, x::AbstractVector) = acq_eval(a, m, x)[1]
+(a::UpperConfidenceBound)(m::CuGradientGP, x::AbstractVector) = acq_eval(a, m, x)[1]
+
+# GradientNormUCB (gradNormUCB.jl:43-51) and EnsembleAcquisition (EnsembleAcq.jl:53-55): all members from ONE posterior
+# pass on the device; the reference calls posterior_grad_mean + posterior_grad_cov once per candidate and per member
+acq_id(::GradientNormUCB) = Int32(3); acq_params(a::GradientNormUCB) = Float64[a.β, 0.0]
+member_params(a) = (p = acq_params(a); length(p) == 2 ? p : Float64[p[1], 0.0])
+function acq_eval_multi(members::Vector, weights::Vector{Float64}, m::Union{CuStandardGP,CuGradientGP}, x::AbstractVector; k::Integer=0)
+    Xc = Matrix{Float64}(points(collect(x))); mcount = size(Xc, 2); nm = length(members)
+    ids = Int32[acq_id(a) for a in members]
+    pars = reduce(hcat, [member_params(a) for a in members])          # 2 x nmem column-major = nmem x 2 row-major
+    scores = Vector{Float64}(undef, mcount)
+    ti = Vector{Int64}(undef, max(k, 1)); tv = Vector{Float64}(undef, max(k, 1))
+    check(GC.@preserve Xc ids weights pars scores ti tv ccall((:abo_acq_eval_multi, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Float64}),
+        m.gpx.h, nm, ids, weights, pars, Xc, mcount, scores, min(k, mcount), ti, tv))
+    scores, ti[1:min(k, mcount)] .+ 1, tv[1:min(k, mcount)]
+end
+(a::GradientNormUCB)(m::CuGradientGP, x::AbstractVector) = acq_eval_multi(Any[a], [1.0], m, x)[1]
+const FusableAcq = Union{ExpectedImprovement,ProbabilityImprovement,UpperConfidenceBound,GradientNormUCB}
+function (ea::EnsembleAcquisition)(m::Union{CuStandardGP,CuGradientGP}, x::AbstractVector)
+    if all(a -> a isa FusableAcq, ea.acquisitions) && length(ea.acquisitions) <= 8
+        return acq_eval_multi(collect(Any, ea.acquisitions), collect(Float64, ea.weights), m, x)[1]
+    end
+    sum([ea.weights[i] .* ea.acquisitions[i](m, x) for i in eachindex(ea.weights)])      # EnsembleAcq.jl:53-55
+end
+
+# nlml(::GradientGP, params, xs, ys) (GradientGP.jl:684-738) incl. ForwardDiff.Dual parameters: xs / ys arrive already
+# prepared by optimize_hyperparameters (prep_input / prep_output, bayesian_opt.jl:250-251): xs the plain points,
+# ys the out-major vector
+function nlml_value_grad(m::CuGradientGP, θ::Vector{Float64}, xs, ys)
+    X = Matrix{Float64}(points(collect(xs))); d, n = size(X); p = m.prior.p
+    y = ys isa AbstractVector{<:Real} ? collect(Float64, ys) : collect(Float64, vec(permutedims(reduce(hcat, ys))))
+    length(y) == n * p || throw(DimensionMismatch("ys must hold n p values"))
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:abo_gp_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}), ctx().h, kernel_id(m), d, p, r))
+    h = Handle(r[]); mc = mean_consts(m, X[:, 1])
+    check(ccall((:abo_gp_set_params, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, Ptr{Float64}),
+        h.h, inv_lengthscale(m), get_scale(m)[1], m.prior.noise_var, mc))
+    val = Ref{Float64}(0.0); g = zeros(2); info = Ref{Int32}(0)
+    check(GC.@preserve X y θ g ccall((:abo_nlml_batch, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ref{Float64}, Ptr{Float64}, Ref{Int32}),
+        h.h, X, y, n, θ, 1, val, g, info))
+    info[] != 0 && throw(LinearAlgebra.PosDefException(info[]))
+    val[], g
+end
+nlml(m::CuGradientGP, p::AbstractVector{<:AbstractFloat}, xs, ys) = nlml_value_grad(m, collect(Float64, p), xs, ys)[1]
+function nlml(m::CuGradientGP, p::AbstractVector{D}, xs, ys) where {T,V,N,D<:ForwardDiff.Dual{T,V,N}}
+    v, g = nlml_value_grad(m, Float64.(ForwardDiff.value.(p)), xs, ys)
+    ForwardDiff.Dual{T}(v, g[1] * ForwardDiff.partials(p[1]) + g[2] * ForwardDiff.partials(p[2]))
+end
+nlml_ls(m::CuGradientGP, log_ℓ, log_scale::Float64, xs, ys) = nlml(m, [log_ℓ, oftype(log_ℓ, log_scale)], xs, ys)
+
+# monte_carlo_fill_distance (src/BO_utils.jl:140-159) on the device; the caller draws the uniform samples
+function fill_distance(X::Matrix{Float64}, S::Matrix{Float64})         # both d x count, column-major = point-major
+    out = Ref{Float64}(0.0)
+    check(GC.@preserve X S ccall((:abo_fill_distance, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Float64}, Int64, Ref{Float64}),
+        ctx().h, X, size(X, 2), size(X, 1), S, size(S, 2), out))
+    out[]
+end
 
 end # module

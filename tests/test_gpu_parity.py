@@ -661,6 +661,35 @@ def test_grad_norm_ucb_and_ensemble(abo, orc):
     dom = abo.ContinuousDomain([-2.0] * 3, [2.0] * 3)
     x = abo.optimize_acquisition(ens, gp, dom, n_grid=500, n_local=2, rng=np.random.default_rng(0))
     assert x.shape == (3,) and np.all(x >= dom.lower) and np.all(x <= dom.upper)
+    # the device top-k of the fused members is sortperm(scores; rev = true)[1:k] of the scores it returns
+    sg, tg, vg = g.topk(gp, Xq, 25)
+    assert list(tg) == list(orc.sortperm_rev(sg, 25)) and np.array_equal(vg, sg[tg]) and np.array_equal(sg, val)
+    # batched refinement (central differences of ONE batched call per step) does not lose to the best grid point
+    xg = abo.optimize_acquisition(g, gp, dom, n_grid=800, n_local=6, rng=np.random.default_rng(3), refine=False)
+    xr = abo.optimize_acquisition(g, gp, dom, n_grid=800, n_local=6, rng=np.random.default_rng(3), refine=True)
+    assert float(g(gp, xr[None, :])[0]) >= float(g(gp, xg[None, :])[0]) - 1e-12
+    # three members incl. PI and UCB share the pass; equals the member-by-member sum
+    pi = abo.ProbabilityImprovement(0.01, float(Y[:, 0].min())); ucb = abo.UpperConfidenceBound(2.0)
+    e3 = abo.EnsembleAcquisition([1.0, 1.0, 2.0, 4.0], [ei, pi, ucb, g])
+    ref3 = 0.125 * ei(gp, Xq[:300]) + 0.125 * pi(gp, Xq[:300]) + 0.25 * ucb(gp, Xq[:300]) + 0.5 * val[:300]
+    assert np.allclose(e3(gp, Xq[:300]), ref3, rtol=1e-12, atol=1e-13)
+    # value-only members on a StandardGP go through the fused sweep once
+    sgp = abo.update(abo.StandardGP(make_kernel(abo, 1, 0.7, 1.2), 1e-4), X, Y[:, 0])
+    e2s = abo.EnsembleAcquisition([1.0, 3.0], [ei, ucb])
+    assert np.allclose(e2s(sgp, Xq[:400]), 0.25 * ei(sgp, Xq[:400]) + 0.75 * ucb(sgp, Xq[:400]), rtol=1e-13, atol=1e-14)
+    with pytest.raises(TypeError):
+        g(sgp, Xq[:4])                                          # GradientNormUCB needs a GradientGP
+
+
+def test_grad_norm_ucb_c3_shape(abo, orc):
+    """d = 10 (p = 11), the C3 kernel family: per-candidate 10 x 10 posterior gradient covariance on the device."""
+    c = orc.make_config("C3", n=60, m=700)
+    gp = abo.update(abo.GradientGP(make_kernel(abo, c["kind"], c["inv_ls"], c["scale"]), 11, c["noise"]), c["X"], c["Y"])
+    post = orc.fit_gradient(c["X"], c["Y"], c["kind"], c["inv_ls"], c["scale"], c["noise"])
+    g = abo.GradientNormUCB(2.0)
+    val = g(gp, c["Xc"])                                        # 700 candidates: two passes of 352
+    ref = orc.grad_norm_ucb(post, c["Xc"][340:370], 2.0)
+    assert np.all(np.isfinite(val)) and close(val[340:370], ref, np.max(np.abs(ref)), 1e-9)
 
 
 # ---- lengthscale_bounds / monte_carlo_fill_distance (BO_utils.jl:87-159; test_bayesian_opt.jl:419-456)
