@@ -210,7 +210,7 @@ constexpr int POTF2_PLD = 132;                                   // sub-panel bu
 // (4+s: D_s final, 8+s: rows below column block s final) that the inverse group syncs on.
 // ------------------------------------------------------------------------------------------
 constexpr int PW_XLD = 36;
-constexpr int PW_F_SCRATCH = 32 * POTF2_PLD + 64 + 32 + 32 * 32;            // panel | col ping-pong | 1/diag | D^T
+constexpr int PW_F_SCRATCH = 32 * POTF2_PLD + 64 + 2 * 32 + 2 * 32 * 32;    // panel | col ping-pong | 1/diag x 2 | D^T x 2 (look-ahead)
 constexpr int PW_I_SCRATCH = 32 * PW_XLD + 3 * 32 * PW_XLD + 320;            // X_ss | S_s0..S_s2 | T of the 32-block levels
 constexpr int PW_SMEM_BYTES = (128 * POTF2_LD + PW_F_SCRATCH + PW_I_SCRATCH + 16) * (int)sizeof(double);
 
@@ -225,9 +225,9 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
     double* sL = sm;                                   // [128][129]
     double* sP = sm + 128 * POTF2_LD;                  // factor group: panel [32][132]
     double* sCol = sP + 32 * POTF2_PLD;                // two 32-entry column buffers
-    double* sRinv = sCol + 64;                         // reciprocals of the current block's diagonal
-    double* sDT = sRinv + 32;                          // transposed diagonal block [32][32]
-    double* sXs = sDT + 32 * 32;                       // inverse group: X_ss [32][36]
+    double* sRinv = sCol + 64;                         // reciprocals of the block's diagonal, two sub-panels (ping-pong)
+    double* sDT = sRinv + 2 * 32;                      // transposed diagonal block [32][32], two sub-panels
+    double* sXs = sDT + 2 * 32 * 32;                   // inverse group: X_ss [32][36]
     double* sS = sXs + 32 * PW_XLD;                    // S_st, t = 0..2, [32][36] each
     double* sTi = sS + 3 * 32 * PW_XLD;                // T staging of the levels inside a 32-block
     __shared__ int s_fail;
@@ -243,18 +243,44 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
     // warps 1..15 stage the block in shared memory; warp 0 takes the first diagonal block D_0 straight
     // from global memory into registers and factors it meanwhile (its result is what everybody waits for)
     if (warp > 0) {
-        for (int e = tid - 32; e < 128 * 128; e += 480) {
-            int r = e >> 7, c = e & 127;
-            if (r >= 32 || c >= 32) sL[r * POTF2_LD + c] = A[(int64_t)r * ld + c];
+        // 16-byte loads, eight in flight per thread before the first shared-memory store: the staging must not be a chain of
+        // dependent global-memory latencies (it gates the first substitution: everybody waits for "block staged AND D_0 final")
+        constexpr int NV = 128 * 64;                       // double2 elements of the block
+        for (int e0 = tid - 32; e0 < NV; e0 += 480 * 8) {
+            double2 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int e = e0 + q * 480;
+                if (e < NV) v[q] = *reinterpret_cast<const double2*>(A + (int64_t)(e >> 6) * ld + 2 * (e & 63));
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int e = e0 + q * 480;
+                if (e < NV) {
+                    const int r = e >> 6, c = 2 * (e & 63);
+                    if (r >= 32 || c >= 32) { sL[r * POTF2_LD + c] = v[q].x; sL[r * POTF2_LD + c + 1] = v[q].y; }
+                }
+            }
         }
     }
     if (stamp) g_potf2_clk[1] = clock64();
 
     if (warp < 8) {
         // =============================== FACTOR GROUP ===============================
+        // Look-ahead inside the block: warp 0 only factors the 32 x 32 diagonal blocks.  As soon as D_sp is final the other
+        // seven warps substitute the rows below it; the three 16 x 16 tiles of the trailing update that make up the NEXT
+        // diagonal block go first (warps 1-3, one tile each) and release warp 0 into diag(sp + 1), which then runs concurrently
+        // with the write-back of column block sp and the rest of the rank-32 update.  The chain per sub-panel is
+        // diag -> substitution -> one tile -> diag instead of diag -> substitution -> write-back -> whole update -> diag.
+        //   named barriers: 1 "D_sp final" (warp 0 arrives, 256) | 3 "panel substituted" (warps 1-7, 224)
+        //                   12 "next diagonal block updated" (warps 1-3 arrive, warp 0 syncs, 128) | 13 "update done" (warps 1-7, 224)
         for (int sp = 0; sp < 4; ++sp) {
             const int c0 = sp * 32, c1 = c0 + 32;
+            double* sDTp = sDT + (sp & 1) * (32 * 32);     // ping-pong: warp 0 runs one sub-panel ahead of the readers
+            double* sRinvp = sRinv + (sp & 1) * 32;
             if (warp == 0) {
+                if (sp > 0) bar_named(12, 128);            // block (c0..c1)^2 carries the updates of all previous sub-panels
+                if (stamp && sp == 1) g_potf2_clk[5] = clock64();
                 double a[32];
                 if (sp == 0) {
 #pragma unroll
@@ -275,7 +301,7 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
                         const double own = fma(-lj, lj, a[(j + 1) & 31]);
                         d = __shfl_sync(0xffffffffu, own, (j + 1) & 31);
                     }
-                    if (lane == j) sRinv[j] = rinv;
+                    if (lane == j) sRinvp[j] = rinv;
                     double* col = sCol + (j & 1) * 32;
                     col[lane] = lj;
                     __syncwarp();
@@ -295,37 +321,49 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
                     for (int c = 0; c < 32; ++c) {
                         // the block's strictly-upper part is zeroed: the inverse group reads it as a full tile
                         sL[(c0 + lane) * POTF2_LD + c0 + c] = (c <= lane) ? a[c] : 0.0;
-                        sDT[c * 32 + lane] = (c <= lane) ? a[c] : 0.0;
+                        sDTp[c * 32 + lane] = (c <= lane) ? a[c] : 0.0;
                     }
                 }
-            }
-            if (sp == 0) {
-                __syncthreads();                           // block staged by warps 1..15 AND D_0 final
-            } else {
-                bar_named(1, 256);                         // D_sp is final for the factor group ...
-                asm volatile("bar.arrive %0, 512;\n" ::"r"(4 + sp) : "memory");   // ... and signalled to the inverse group (never waits for it)
-            }
-            if (s_fail) break;
-            if (c1 >= 128) {                               // last column block: its rows are final now
-                for (int e = tid; e < 128 * 32; e += 256) {
-                    const int r = e >> 5, cc = c0 + (e & 31);
-                    A[(int64_t)r * ld + cc] = (cc <= r) ? sL[r * POTF2_LD + cc] : 0.0;
+                if (stamp && sp < 2) g_potf2_clk[sp == 0 ? 4 : 9] = clock64();     // diagonal block of sub-panel sp factored
+                if (sp == 0) __syncthreads();              // block staged by warps 1..15 AND D_0 final
+                else {
+                    __threadfence_block();
+                    asm volatile("bar.arrive 1, 256;\n" ::: "memory");                          // D_sp final for warps 1-7 (not waited for)
+                    asm volatile("bar.arrive %0, 512;\n" ::"r"(4 + sp) : "memory");             // ... and for the inverse group
                 }
-                break;
+                if (s_fail) break;
+                if (c1 >= 128) {                           // last diagonal block: its rows are final, write them back
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) A[(int64_t)(c0 + lane) * ld + c0 + c] = (c <= lane) ? a[c] : 0.0;
+                    break;
+                }
+                // column block sp is written back by the other warps; this arrival only completes the count
+                asm volatile("bar.arrive %0, 512;\n" ::"r"(8 + sp) : "memory");
+                continue;
             }
+            // ------------------------------- warps 1..7 -------------------------------
+            if (sp == 0) __syncthreads();
+            else {
+                bar_named(1, 256);
+                asm volatile("bar.arrive %0, 512;\n" ::"r"(4 + sp) : "memory");
+            }
+            if (tid == 32 && blockIdx.x == 0 && sp == 0) g_potf2_clk[15] = clock64();
+            if (s_fail) break;
+            if (c1 >= 128) break;                          // nothing below the last diagonal block
             {
+                // rows c1 .. 127 over the 224 threads: warp 1 owns the rows of the next diagonal block
                 const int r = c1 + (warp - 1) * 32 + lane;
-                if (warp >= 1 && r < 128) {
+                if (r < 128) {
                     double x[32];
 #pragma unroll
                     for (int c = 0; c < 32; ++c) x[c] = sL[r * POTF2_LD + c0 + c];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        x[j] *= sRinv[j];
+                        x[j] *= sRinvp[j];
 #pragma unroll
                         for (int c2 = 0; c2 < 16; ++c2) {
                             if (2 * c2 + 1 > j) {
-                                const double2 lc = *reinterpret_cast<const double2*>(sDT + j * 32 + 2 * c2);
+                                const double2 lc = *reinterpret_cast<const double2*>(sDTp + j * 32 + 2 * c2);
                                 if (2 * c2 > j) x[2 * c2] = fma(-x[j], lc.x, x[2 * c2]);
                                 x[2 * c2 + 1] = fma(-x[j], lc.y, x[2 * c2 + 1]);
                             }
@@ -335,17 +373,12 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
                     for (int c = 0; c < 32; ++c) { sL[r * POTF2_LD + c0 + c] = x[c]; sP[c * POTF2_PLD + r] = x[c]; }
                 }
             }
-            bar_named(1, 256);
-            for (int e = tid; e < 128 * 32; e += 256) {    // column block sp of L is final: write it back now
-                const int r = e >> 5, cc = c0 + (e & 31);
-                A[(int64_t)r * ld + cc] = (cc <= r) ? sL[r * POTF2_LD + cc] : 0.0;
-            }
-            // rows below column block sp are final AND D_sp has been written back: the inverse group may read
-            // the former and overwrite the latter (it parks X_sp,sp there)
-            asm volatile("bar.arrive %0, 512;\n" ::"r"(8 + sp) : "memory");
+            if (tid == 32 && blockIdx.x == 0 && sp == 0) g_potf2_clk[7] = clock64();
+            bar_named(3, 224);                             // panel (and its transpose sP) complete
+            if (tid == 32 && blockIdx.x == 0 && sp == 0) g_potf2_clk[8] = clock64();
             const int nt = (128 - c1) / 16;
-            const int ntile = nt * (nt + 1) / 2;
-            for (int t = warp; t < ntile; t += 8) {
+            const int ntile = nt * (nt + 1) / 2;           // >= 3; tiles 0, 1, 2 = the next diagonal block (c1 .. c1+32)^2
+            auto update_tile = [&](int t) {
                 int ti = 0, acc_t = t;
                 while (acc_t > ti) { acc_t -= ti + 1; ++ti; }
                 const int tj = acc_t;
@@ -353,15 +386,15 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
                 double cacc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
-                    double a[2], b[2];
+                    double a[2], bq[2];
 #pragma unroll
                     for (int mi = 0; mi < 2; ++mi) a[mi] = sP[(4 * kk + fk) * POTF2_PLD + r0 + 8 * mi + fr];
 #pragma unroll
-                    for (int ni = 0; ni < 2; ++ni) b[ni] = sP[(4 * kk + fk) * POTF2_PLD + q0 + 8 * ni + fr];
+                    for (int ni = 0; ni < 2; ++ni) bq[ni] = sP[(4 * kk + fk) * POTF2_PLD + q0 + 8 * ni + fr];
 #pragma unroll
                     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                        for (int ni = 0; ni < 2; ++ni) dmma8x8x4(cacc[mi][ni][0], cacc[mi][ni][1], a[mi], b[ni]);
+                        for (int ni = 0; ni < 2; ++ni) dmma8x8x4(cacc[mi][ni][0], cacc[mi][ni][1], a[mi], bq[ni]);
                 }
 #pragma unroll
                 for (int mi = 0; mi < 2; ++mi)
@@ -371,8 +404,25 @@ __global__ void __launch_bounds__(512) potf2_ws_kernel(double* __restrict__ Ablk
                         dst[0] -= cacc[mi][ni][0];
                         dst[1] -= cacc[mi][ni][1];
                     }
+            };
+            if (warp <= 3) {                               // the critical tiles first, then warp 0 is released
+                update_tile(warp - 1);
+                if (tid == 32 && blockIdx.x == 0 && sp == 0) g_potf2_clk[10] = clock64();
+                __threadfence_block();
+                asm volatile("bar.arrive 12, 128;\n" ::: "memory");
             }
-            bar_named(1, 256);
+            // column block sp of L is final: write it back (rows c0 .. 127; the diagonal block's upper part as zeros)
+            for (int e = tid - 32; e < 128 * 32; e += 224) {
+                const int r = e >> 5, cc = c0 + (e & 31);
+                A[(int64_t)r * ld + cc] = (cc <= r) ? sL[r * POTF2_LD + cc] : 0.0;
+            }
+            // rows below column block sp are final AND D_sp has been written back: the inverse group may read the former and
+            // overwrite the latter (it parks X_sp,sp there)
+            asm volatile("bar.arrive %0, 512;\n" ::"r"(8 + sp) : "memory");
+            for (int t = (warp <= 3 ? warp - 1 + 7 : warp - 1); t < ntile; t += 7)
+                if (t >= 3) update_tile(t);
+            bar_named(13, 224);                            // whole trailing update done: the next substitution may read it / reuse sP
+            if (stamp && false) g_potf2_clk[7] = clock64();
         }
         if (stamp) { g_potf2_clk[2] = clock64(); g_potf2_clk[3] = g_potf2_clk[2]; }
     } else {

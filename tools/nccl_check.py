@@ -52,6 +52,22 @@ tg = torch.from_numpy(mu_g).cuda(); rg = tg.clone(); dist.broadcast(rg, 0)
 assert torch.equal(tg, rg), "GradientGP posterior differs between ranks after sync + block append"
 full = abo.update(abo.GradientGP(kg, 5, c3["noise"], ctx=ctx), c3["X"], c3["Y"])
 assert np.max(np.abs(mu_g - abo.posterior_grad_mean(full, c3["Xc"][:100]))) < 1e-9
+# the outcome of abo_gp_sync is collective: an un-fitted root, or a receiver created with another dimension, makes EVERY
+# rank return an error instead of leaving its peers blocked inside the broadcast
+unf = abo.empty_posterior_like(abo.StandardGP(abo.SqExponentialKernel(), 0.1, ctx=ctx), 20)
+try:
+    unf.gpx.sync(0); raised = False
+except abo.AboCudaError as e:
+    raised = "no posterior" in str(e)
+assert raised, "un-fitted root must fail on every rank"
+wrong = abo.empty_posterior_like(abo.StandardGP(abo.SqExponentialKernel(), 0.1, ctx=ctx), 20 if rank == 0 else 7)
+src = model.gpx if rank == 0 else wrong.gpx
+try:
+    src.sync(0); raised = False
+except (abo.DimensionMismatch, abo.AboCudaError) as e:
+    raised = True
+assert raised, "a receiver of the wrong dimension must fail the sync on every rank"
+abo.sync_posterior(model, 0)                                  # and the communicator is still usable afterwards
 if rank == 0:
     s_all, ti_all, tv_all = acq.topk(model, c["Xc"], 100)
     assert list(ti_all) == list(gi), "sharded top-k differs from the single-GPU top-k"

@@ -24,4 +24,6 @@ for n in sizes:
     ck = ctx.potf2_clocks()        # stamps of CTA 0 of the last potf2 launch: 0 start, 1 staged, 2 factor group done, 6 end, 11-14 last inverse round
     print("   potf2 (cycles): staged", ck[1] - ck[0], "| factor group done", ck[2] - ck[0], "| inverse round 3: X_33", ck[13] - ck[12],
           "multiply+store", ck[14] - ck[13], "| kernel end", ck[6] - ck[0])
+    print("   diag 0 done", ck[4] - ck[0], "| warp 1 released", ck[15] - ck[0], "| substituted", ck[7] - ck[0], "| panel barrier", ck[8] - ck[0],
+          "| critical tile", ck[10] - ck[0], "| diag 1 starts", ck[5] - ck[0], "| diag 1 done", ck[9] - ck[0])
     print(f"n={n} potrf {best:.3f} ms  {fl / best / 1e9:.2f} TFLOP/s  relres={err:.2e}", flush=True)
