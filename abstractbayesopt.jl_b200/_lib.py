@@ -19,7 +19,7 @@ SYMBOLS = [
     "abo_ctx_launch_count", "abo_ctx_profile", "abo_ctx_profile_read", "abo_debug_potf2_clocks", "abo_gp_create", "abo_gp_destroy", "abo_gp_set_params", "abo_gp_fit", "abo_gp_append",
     "abo_gp_clone", "abo_gp_n", "abo_gp_alpha", "abo_gp_factor", "abo_gp_posterior", "abo_gp_posterior_cov", "abo_acq_eval", "abo_acq_eval_dev", "abo_acq_eval_grad",
     "abo_nlml_batch", "abo_potrf_dev", "abo_fill_distance", "abo_nccl_unique_id", "abo_ctx_init_rank", "abo_gp_sync",
-    "abo_topk_allgather", "abo_allgather_f64", "abo_ctx_ranks", "abo_ctx_trim", "abo_acq_eval_multi",
+    "abo_topk_allgather", "abo_allgather_f64", "abo_ctx_ranks", "abo_ctx_trim", "abo_acq_eval_multi", "abo_standardize",
 ]
 
 
@@ -83,6 +83,7 @@ def lib():
             "abo_nlml_batch": [vp, vp, vp, i64, vp, i64, vp, vp, vp],
             "abo_potrf_dev": [vp, vp, i64, i64, C.POINTER(i64)],
             "abo_fill_distance": [vp, vp, i64, i32, vp, i64, C.POINTER(C.c_double)],
+            "abo_standardize": [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(C.c_double)],
             "abo_nccl_unique_id": [vp],
             "abo_ctx_init_rank": [vp, i32, i32, vp],
             "abo_gp_sync": [vp, i32],
@@ -155,6 +156,16 @@ class Context:
         out = C.c_double(0.0)
         check(lib().abo_fill_distance(self._h, ptr(X), X.shape[0], X.shape[1], ptr(S), S.shape[0], C.byref(out)))
         return out.value
+
+    def standardize(self, y_flat, n: int, p: int, choice: str):
+        """get_mean_std + std_y on the device; returns (mu[p], sd[p], y_std (out-major), min of the standardised values)."""
+        code = {"mean_scale": 0, "scale_only": 1, "mean_only": 2}[choice]
+        y = f64(np.ravel(y_flat))
+        if y.size != n * p:
+            raise DimensionMismatch("ys length does not match n * p")
+        mu = np.empty(p); sd = np.empty(p); ys = np.empty(n * p); best = C.c_double(0.0)
+        check(lib().abo_standardize(self._h, ptr(y), n, p, code, ptr(mu), ptr(sd), ptr(ys), C.byref(best)))
+        return mu, sd, ys, best.value
 
     def potf2_clocks(self):
         out = (C.c_int64 * 16)()

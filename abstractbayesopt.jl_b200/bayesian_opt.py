@@ -248,10 +248,25 @@ def stop_criteria(BO):
 
 
 def standardize_problem(BO, choice):
-    """standardize_problem (BO_utils.jl:44-64)."""
-    mu, sd = get_mean_std(BO.model, np.array(BO.ys_non_std), choice)
-    BO.model = rescale_model(BO.model, sd)
-    BO.ys = list(std_y(BO.model, np.array(BO.ys_non_std), mu, sd))
+    """standardize_problem (BO_utils.jl:44-64).  The empirical mean / standard deviation, the standardised observations
+    and the new incumbent come from ONE device call (abo_standardize); rescale_model stays a host-side parameter update."""
+    if choice not in ("mean_scale", "scale_only", "mean_only"):
+        raise ValueError("choice must be one of: 'mean_scale', 'scale_only', 'mean_only'")
+    from ._lib import default_context
+    is_grad = isinstance(BO.model, GradientGP)
+    Y = np.asarray(BO.ys_non_std, dtype=np.float64)
+    n = len(BO.ys_non_std)
+    p = BO.model.p
+    flat = Y.T.reshape(-1) if is_grad else Y.reshape(-1)              # out-major (prep_output)
+    mu_v, sd_v, y_std, _best = (BO.model.ctx or default_context()).standardize(flat, n, p, choice)
+    if is_grad:
+        mu, sd = mu_v, sd_v
+        BO.ys = list(y_std.reshape(p, n).T)
+    else:
+        mu, sd = float(mu_v[0]), float(sd_v[0])
+        BO.ys = list(y_std)
+    if choice in ("scale_only", "mean_scale"):
+        BO.model = rescale_model(BO.model, sd)
     BO.model = update_surrogate(BO.model, np.array(BO.xs), np.array(BO.ys))
     BO.acq = BO.acq.update(np.array(BO.ys), BO.model)
     return BO, (mu, sd)

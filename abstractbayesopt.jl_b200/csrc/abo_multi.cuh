@@ -72,3 +72,70 @@ extern "C" int32_t abo_acq_eval_multi(abo_gp* g, int32_t nmem, const int32_t* ac
     }
     return scores_select_readback(c, dS, m, scores, k, top_idx, top_val);
 }
+
+// ------------------------------------------------------------------------------------------
+// abo_standardize — get_mean_std + std_y of standardize_problem (src/BO_utils.jl:44-64, StandardGP.jl:164-204,
+// GradientGP.jl:756-783) on the device: mean (pairwise tree), corrected sample standard deviation (two-pass), the
+// standardised observations and the incumbent min of the standardised value output, one launch.
+//   StandardGP (p = 1): y_std = (y - mu) / sd.   GradientGP: mu = (mean of the VALUE output, 0, ...), sd = std of the value
+//   output for every output; y_std[a] = (y[a] - mu[a]) / sd[0].   choice: 0 mean_scale, 1 scale_only (mu = 0), 2 mean_only (sd = 1).
+// ------------------------------------------------------------------------------------------
+namespace abo {
+__global__ void __launch_bounds__(1024) standardize_kernel(const double* __restrict__ y, int64_t n, int p, int choice,
+                                                           double* __restrict__ y_std, double* __restrict__ out /* mu, sd, best */) {
+    __shared__ double sh[1024];
+    __shared__ double s_mu, s_sd;
+    const int t = threadIdx.x;
+    auto reduce = [&](double v, bool take_min) {
+        sh[t] = v;
+        __syncthreads();
+        for (int o = 512; o > 0; o >>= 1) {
+            if (t < o) sh[t] = take_min ? fmin(sh[t], sh[t + o]) : sh[t] + sh[t + o];
+            __syncthreads();
+        }
+        const double r = sh[0];
+        __syncthreads();
+        return r;
+    };
+    double acc = 0.0;
+    for (int64_t i = t; i < n; i += 1024) acc += y[i];                  // value output = the first n entries (out-major)
+    const double mean = reduce(acc, false) / (double)n;
+    acc = 0.0;
+    for (int64_t i = t; i < n; i += 1024) { const double dv = y[i] - mean; acc = fma(dv, dv, acc); }
+    const double sd_raw = sqrt(reduce(acc, false) / (double)(n - 1));
+    if (t == 0) { s_mu = (choice == 1) ? 0.0 : mean; s_sd = (choice == 2) ? 1.0 : sd_raw; }
+    __syncthreads();
+    const double mu = s_mu, sd = s_sd;
+    double best = CUDART_INF;
+    for (int64_t i = t; i < n * p; i += 1024) {
+        const double v = (y[i] - (i < n ? mu : 0.0)) / sd;
+        y_std[i] = v;
+        if (i < n) best = fmin(best, v);
+    }
+    best = reduce(best, true);
+    if (t == 0) { out[0] = mu; out[1] = sd; out[2] = best; }
+}
+}  // namespace abo
+
+extern "C" int32_t abo_standardize(abo_ctx* c, const double* y, int64_t n, int32_t p, int32_t choice, double* mu, double* sd,
+                                   double* y_std, double* best) {
+    if (!c || !y || !mu || !sd || !y_std) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (n < 2 || p < 1) return abo_fail(ABO_ERR_DIM, "standardisation needs at least two observations");
+    if (choice < 0 || choice > 2) return abo_fail(ABO_ERR_INVALID, "choice must be 0 (mean_scale), 1 (scale_only) or 2 (mean_only)");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    double *dy, *dout;
+    int rc;
+    if ((rc = ws_get(c, WS_STAGE_Y, sizeof(double) * (size_t)(2 * n * p + 8), (void**)&dy))) return rc;
+    dout = dy + 2 * n * p;
+    CU(cudaMemcpyAsync(dy, y, sizeof(double) * n * p, cudaMemcpyHostToDevice, st));
+    standardize_kernel<<<1, 1024, 0, st>>>(dy, n, p, choice, dy + n * p, dout);
+    KL(c);
+    double h[3];
+    CU(cudaMemcpyAsync(y_std, dy + n * p, sizeof(double) * n * p, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h, dout, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int a = 0; a < p; ++a) { mu[a] = a == 0 ? h[0] : 0.0; sd[a] = h[1]; }
+    if (best) *best = h[2];
+    return ABO_OK;
+}

@@ -166,6 +166,14 @@ int32_t abo_nlml_batch(abo_gp* gp, const double* X, const double* y, int64_t n,
 int32_t abo_fill_distance(abo_ctx* ctx, const double* X, int64_t n, int32_t d, const double* S, int64_t m,
                           double* h_fill);
 
+/* get_mean_std + std_y of standardize_problem (src/BO_utils.jl:44-64; StandardGP.jl:164-204, GradientGP.jl:756-783) on the
+ * device.  y: n*p observations, out-major; choice 0 "mean_scale", 1 "scale_only" (mu = 0), 2 "mean_only" (sd = 1).
+ * mu[p], sd[p]: the empirical mean of the VALUE output (0 for gradient outputs) and its corrected sample standard deviation
+ * (the same for every output); y_std[n*p] = (y - mu) / sd[0]; *best (nullable) = minimum of the standardised value output,
+ * the incumbent update(acq, ys, model) needs (ExpectedImprovement.jl:81-83). */
+int32_t abo_standardize(abo_ctx* ctx, const double* y, int64_t n, int32_t p, int32_t choice, double* mu, double* sd,
+                        double* y_std, double* best);
+
 /* ---- standalone factorisation entry (Cholesky TFLOP/s metric; A is n x n row-major, lower
  *      triangle referenced, overwritten by L on device; d_A device pointer, ld >= n) ---------- */
 int32_t abo_potrf_dev(abo_ctx* ctx, double* d_A, int64_t n, int64_t ld, int64_t* info);

@@ -348,6 +348,20 @@ function nlml(m::CuGradientGP, p::AbstractVector{D}, xs, ys) where {T,V,N,D<:For
 end
 nlml_ls(m::CuGradientGP, log_ℓ, log_scale::Float64, xs, ys) = nlml(m, [log_ℓ, oftype(log_ℓ, log_scale)], xs, ys)
 
+# get_mean_std + std_y of standardize_problem (src/BO_utils.jl:44-64) in one device call: (μ, σ, standardised ys, incumbent).
+# `ys` as the BO loop holds them (Vector{Float64} or Vector{Vector{Float64}}); returns ys in the same shape.
+const STD_CHOICE = Dict("mean_scale" => Int32(0), "scale_only" => Int32(1), "mean_only" => Int32(2))
+function standardize_device(m::Union{CuStandardGP,CuGradientGP}, ys::AbstractVector, choice::String)
+    grad = m isa CuGradientGP
+    p = grad ? m.prior.p : 1; n = length(ys)
+    y = grad ? collect(Float64, vec(permutedims(reduce(hcat, ys)))) : collect(Float64, ys)    # out-major
+    μ = Vector{Float64}(undef, p); σ = Vector{Float64}(undef, p); ystd = similar(y); best = Ref{Float64}(0.0)
+    check(GC.@preserve y μ σ ystd ccall((:abo_standardize, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+        ctx().h, y, n, p, STD_CHOICE[choice], μ, σ, ystd, best))
+    grad ? (μ, σ, [collect(r) for r in eachrow(reshape(ystd, n, p))], best[]) : (μ[1], σ[1], ystd, best[])
+end
+
 # monte_carlo_fill_distance (src/BO_utils.jl:140-159) on the device; the caller draws the uniform samples
 function fill_distance(X::Matrix{Float64}, S::Matrix{Float64})         # both d x count, column-major = point-major
     out = Ref{Float64}(0.0)

@@ -187,3 +187,27 @@ def test_update_bo_wrong_dimension_gradient_gp(abo):
     bo = abo.BOStruct(f, abo.ExpectedImprovement(0.01, 2.0), gp, dom, xs, ys, 10, 0.0)
     with pytest.raises(abo.DimensionMismatch):
         abo.update(bo, [0.0], f([0.0]), 0)
+
+
+# ---- get_mean_std / std_y on the device (BO_utils.jl:44-64, StandardGP.jl:164-204, GradientGP.jl:756-783) ----------
+@pytest.mark.parametrize("choice", ["mean_scale", "scale_only", "mean_only"])
+def test_device_standardisation_matches_reference_formulas(abo, choice):
+    rng = np.random.default_rng(11)
+    ctx = abo.default_context()
+    y = 3.0 + 2.5 * rng.standard_normal(5000)
+    mu, sd, ys, best = ctx.standardize(y, len(y), 1, choice)
+    mu_ref = 0.0 if choice == "scale_only" else float(np.mean(y))
+    sd_ref = 1.0 if choice == "mean_only" else float(np.std(y, ddof=1))          # Statistics.std: corrected
+    assert abs(mu[0] - mu_ref) <= 1e-14 * max(1.0, abs(mu_ref)) and abs(sd[0] - sd_ref) <= 1e-14 * sd_ref
+    assert np.max(np.abs(ys - (y - mu_ref) / sd_ref)) <= 1e-13 and best == ys.min()
+    # GradientGP: only the value output is centred, every output is divided by the value output's std
+    Y = np.column_stack([y[:400], rng.standard_normal((400, 3))])
+    mu_g, sd_g, ys_g, best_g = ctx.standardize(Y.T.reshape(-1), 400, 4, choice)
+    m0 = 0.0 if choice == "scale_only" else float(np.mean(Y[:, 0])); s0 = 1.0 if choice == "mean_only" else float(np.std(Y[:, 0], ddof=1))
+    assert np.allclose(mu_g, [m0, 0, 0, 0], rtol=0, atol=1e-14) and np.allclose(sd_g, s0, rtol=1e-14, atol=0)
+    ref = (Y - np.array([m0, 0, 0, 0])[None, :]) / s0
+    assert np.max(np.abs(ys_g.reshape(4, 400).T - ref)) <= 1e-13 and best_g == ys_g[:400].min()
+    # the host helpers the reference's loop calls give the same numbers
+    g = abo.StandardGP(abo.SqExponentialKernel(), 1e-6)
+    mu_h, sd_h = abo.get_mean_std(g, y, choice)
+    assert abs(mu_h - mu[0]) <= 1e-14 * max(1.0, abs(mu_h)) and abs(sd_h - sd[0]) <= 1e-14 * sd_h
