@@ -8,7 +8,7 @@ from .kernels import (ADMatern52Kernel, ADMatern72Kernel, ApproxMatern52Kernel, 
                       Matern52Kernel, Matern72Kernel, SqExponentialKernel, with_lengthscale,
                       extract_scale_and_lengthscale)
 from .surrogates import (AbstractSurrogate, GradientGP, StandardGP, get_kernel_constructor, get_lengthscale,
-                         get_mean_std, get_scale, nlml, nlml_batch, nlml_ls, posterior_grad_mean,
+                         get_mean_std, get_scale, is_ard, nlml, nlml_batch, nlml_ls, posterior_grad_mean,
                          posterior_grad_var, posterior_grad_cov, posterior_cov, posterior_mean, posterior_var, prep_input, prep_output, rescale_model,
                          std_y, unstandardized_mean_and_var, update_surrogate, empty_posterior_like, _get_minimum,
                          _update_model_parameters)

@@ -19,7 +19,7 @@ SYMBOLS = [
     "abo_ctx_launch_count", "abo_ctx_profile", "abo_ctx_profile_read", "abo_debug_potf2_clocks", "abo_gp_create", "abo_gp_destroy", "abo_gp_set_params", "abo_gp_fit", "abo_gp_append",
     "abo_gp_clone", "abo_gp_n", "abo_gp_alpha", "abo_gp_factor", "abo_gp_posterior", "abo_gp_posterior_cov", "abo_acq_eval", "abo_acq_eval_dev", "abo_acq_eval_grad",
     "abo_nlml_batch", "abo_potrf_dev", "abo_fill_distance", "abo_nccl_unique_id", "abo_ctx_init_rank", "abo_gp_sync",
-    "abo_topk_allgather", "abo_allgather_f64", "abo_ctx_ranks", "abo_ctx_trim", "abo_acq_eval_multi", "abo_standardize",
+    "abo_topk_allgather", "abo_allgather_f64", "abo_ctx_ranks", "abo_ctx_trim", "abo_acq_eval_multi", "abo_standardize", "abo_gp_set_params_ard", "abo_nlml_batch_ard",
 ]
 
 
@@ -68,6 +68,7 @@ def lib():
             "abo_gp_create": [vp, i32, i32, i32, C.POINTER(vp)],
             "abo_gp_destroy": [vp],
             "abo_gp_set_params": [vp, dbl, dbl, dbl, vp],
+            "abo_gp_set_params_ard": [vp, vp, dbl, dbl, vp],
             "abo_gp_fit": [vp, vp, vp, i64, C.POINTER(i64)],
             "abo_gp_append": [vp, vp, vp, C.POINTER(i64)],
             "abo_gp_clone": [vp, C.POINTER(vp)],
@@ -81,6 +82,7 @@ def lib():
             "abo_acq_eval_multi": [vp, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp],
             "abo_acq_eval_grad": [vp, i32, vp, vp, i64, vp, vp, vp, vp],
             "abo_nlml_batch": [vp, vp, vp, i64, vp, i64, vp, vp, vp],
+            "abo_nlml_batch_ard": [vp, vp, vp, i64, vp, i64, vp, vp, vp],
             "abo_potrf_dev": [vp, vp, i64, i64, C.POINTER(i64)],
             "abo_fill_distance": [vp, vp, i64, i32, vp, i64, C.POINTER(C.c_double)],
             "abo_standardize": [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(C.c_double)],
@@ -255,7 +257,13 @@ class GpHandle:
         mc = None if mean_c is None else f64(np.atleast_1d(mean_c))
         if mc is not None and mc.size != self.p:
             raise DimensionMismatch("mean_c must have p entries")
-        check(lib().abo_gp_set_params(self._h, float(inv_ls), float(scale), float(noise), ptr(mc)))
+        if np.ndim(inv_ls) > 0:                               # ARD: one inverse length scale per dimension
+            sv = f64(np.ravel(inv_ls))
+            if sv.size != self.d:
+                raise DimensionMismatch(f"ARD kernel has {sv.size} length scales, the data have dimension {self.d}")
+            check(lib().abo_gp_set_params_ard(self._h, ptr(sv), float(scale), float(noise), ptr(mc)))
+        else:
+            check(lib().abo_gp_set_params(self._h, float(inv_ls), float(scale), float(noise), ptr(mc)))
 
     def fit(self, X, y_flat):
         X = f64(X); y = f64(y_flat)
@@ -363,14 +371,19 @@ class GpHandle:
                                      C.c_void_p(d_scores) if d_scores else None, k, ptr(ti), ptr(tv)))
         return ti[:k], tv[:k]
 
-    def nlml_batch(self, X, y_flat, logparams, want_grad=True):
+    def nlml_batch(self, X, y_flat, logparams, want_grad=True, ard=False):
+        """ard=False: rows {log l, log sig2}; ard=True: rows {log l_1 .. log l_d, log sig2}."""
         X = f64(X); y = f64(y_flat); lp = f64(np.atleast_2d(logparams))
         n = X.shape[0]; R = lp.shape[0]
+        npar = self.d + 1 if ard else 2
+        if lp.shape[1] != npar:
+            raise DimensionMismatch(f"parameter vectors must have {npar} entries")
         if y.size != n * self.p:
             raise DimensionMismatch("ys length does not match xs")
-        val = np.empty(R); grad = np.empty((R, 2)) if want_grad else None
+        val = np.empty(R); grad = np.empty((R, npar)) if want_grad else None
         info = np.zeros(R, dtype=np.int32)
-        check(lib().abo_nlml_batch(self._h, ptr(X), ptr(y), n, ptr(lp), R, ptr(val), ptr(grad), ptr(info)))
+        fn = lib().abo_nlml_batch_ard if ard else lib().abo_nlml_batch
+        check(fn(self._h, ptr(X), ptr(y), n, ptr(lp), R, ptr(val), ptr(grad), ptr(info)))
         return val, grad, info
 
     def sync(self, root=0):

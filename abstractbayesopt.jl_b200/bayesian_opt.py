@@ -169,11 +169,14 @@ def lockstep_lbfgsb(fg, x0, lower, upper, g_tol=1e-6, f_abstol=2.2e-9, max_iter=
 
 
 def optimize_hyperparameters(model, x_train, y_train, old_params, scale_std=1.0, length_scale_only=False,
-                             num_restarts=1, domain=None, rng=None, max_iter=100):
+                             num_restarts=1, domain=None, rng=None, max_iter=100, ard=False):
     """optimize_hyperparameters (bayesian_opt.jl:196-328).  Same log-space box, clamped start and
     uniform random restarts; all restarts advance in LOCK-STEP so that every objective/gradient
     evaluation is ONE batched abo_nlml_batch call (value + analytic gradient for all restarts) instead
-    of one ForwardDiff evaluation per restart and step."""
+    of one ForwardDiff evaluation per restart and step.
+    ard=True optimises one length scale per input dimension, params = (log l_1 .. log l_d, log sig2) — the extension
+    of the nlml parameter vector the reference lists as a TODO (bayesian_opt.jl:193-194); `old_params` may be the
+    isotropic pair (replicated) or the full vector."""
     rng = np.random.default_rng() if rng is None else rng
     ls_lo, ls_hi = 1e-3, 1e3
     if domain is not None:                               # data-informed bounds (bayesian_opt.jl:216-228)
@@ -181,20 +184,24 @@ def optimize_hyperparameters(model, x_train, y_train, old_params, scale_std=1.0,
         ls_lo, ls_hi = max(float(np.min(lL)), 1e-6), float(np.max(lU))
         assert ls_lo < ls_hi
     sc_lo, sc_hi = 1e-3 / scale_std ** 2, 1e6 / scale_std ** 2
-    lo = np.log([ls_lo, sc_lo]); hi = np.log([ls_hi, sc_hi])
+    nd = np.asarray(x_train, dtype=np.float64).reshape(len(x_train), -1).shape[1] if ard else 1
+    lo = np.log([ls_lo] * nd + [sc_lo]); hi = np.log([ls_hi] * nd + [sc_hi])
+    old = np.asarray(old_params, dtype=np.float64).reshape(-1)
+    if ard and old.size == 2:
+        old = np.concatenate([np.full(nd, old[0]), old[1:]])
     eps2 = 2 * np.finfo(float).eps
-    start = np.clip(np.asarray(old_params, dtype=np.float64), lo + eps2, hi - eps2)      # bayesian_opt.jl:248
-    inits = np.array([start] + [lo + (hi - lo) * rng.random(2) for _ in range(num_restarts - 1)])
+    start = np.clip(old, lo + eps2, hi - eps2)                                             # bayesian_opt.jl:248
+    inits = np.array([start] + [lo + (hi - lo) * rng.random(nd + 1) for _ in range(num_restarts - 1)])
     lower, upper = lo.copy(), hi.copy()
     if length_scale_only:                                  # nlml_ls: log scale frozen at the start value
-        inits[:, 1] = start[1]; lower[1] = upper[1] = start[1]
+        inits[:, -1] = start[-1]; lower[-1] = upper[-1] = start[-1]
 
     def fg(X, idx):
-        val, grad, info = nlml_batch(model, X[idx], x_train, y_train)
+        val, grad, info = nlml_batch(model, X[idx], x_train, y_train, ard=ard)
         val = np.where(info != 0, np.inf, val)
         grad = np.where(np.isfinite(grad), grad, 0.0)
         if length_scale_only:
-            grad[:, 1] = 0.0
+            grad[:, -1] = 0.0
         return val, grad
 
     X, f, converged, failed = lockstep_lbfgsb(fg, inits, lower, upper, max_iter=max_iter)
@@ -203,8 +210,8 @@ def optimize_hyperparameters(model, x_train, y_train, old_params, scale_std=1.0,
         log.info("All restarts failed to converge.")
         return model
     best = X[np.flatnonzero(good)[np.argmin(f[good])]]
-    ell = math.exp(best[0])
-    scale = get_scale(model)[0] if length_scale_only else math.exp(best[1])
+    ell = np.exp(best[:nd]) if ard else math.exp(best[0])
+    scale = get_scale(model)[0] if length_scale_only else math.exp(best[-1])
     k_opt = scale * with_lengthscale(get_kernel_constructor(model), ell)
     return _update_model_parameters(model, k_opt)
 
@@ -273,7 +280,7 @@ def standardize_problem(BO, choice):
 
 
 def optimize(BO: BOStruct, standardize="mean_scale", hyper_params="all", num_restarts_HP=1, n_grid=10_000,
-             n_local=100, rng=None, refine=True):
+             n_local=100, rng=None, refine=True, ard=False):
     """optimize(BO; standardize, hyper_params, num_restarts_HP) (bayesian_opt.jl:364-449)."""
     if standardize not in ("mean_scale", "scale_only", "mean_only", None):
         raise ValueError("standardize must be one of mean_scale, scale_only, mean_only, None")
@@ -291,11 +298,12 @@ def optimize(BO: BOStruct, standardize="mean_scale", hyper_params="all", num_res
     i = 0
     while not stop_criteria(BO) and not BO.flag:
         if hyper_params is not None and i % 10 == 0:
-            old = [math.log(get_lengthscale(BO.model)[0]), math.log(get_scale(BO.model)[0])]
+            ls = get_lengthscale(BO.model)
+            old = [math.log(v) for v in (ls if ard and len(ls) > 1 else ls[:1])] + [math.log(get_scale(BO.model)[0])]
             m2 = optimize_hyperparameters(BO.model, np.array(BO.xs), np.array(BO.ys), old,
                                           scale_std=float(np.ravel(sd)[0]),
                                           length_scale_only=(hyper_params == "length_scale_only"),
-                                          num_restarts=num_restarts_HP, domain=BO.domain, rng=rng)
+                                          num_restarts=num_restarts_HP, domain=BO.domain, rng=rng, ard=ard)
             BO.model = update_surrogate(m2, np.array(BO.xs), np.array(BO.ys))
         x_cand = optimize_acquisition(BO.acq, BO.model, BO.domain, n_grid=n_grid, n_local=n_local, rng=rng,
                                       refine=refine)

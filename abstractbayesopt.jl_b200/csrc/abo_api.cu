@@ -718,6 +718,7 @@ extern "C" int32_t abo_gp_create(abo_ctx* ctx, int32_t kernel_id, int32_t d, int
     if (!g) return abo_fail(ABO_ERR_ALLOC, "host allocation failed");
     g->ctx = ctx; g->kind = kernel_id; g->d = d; g->p = p;
     g->s = 1.0; g->scale = 1.0; g->noise = 0.0;
+    g->sv.assign(d, 1.0); g->ard = false;
     g->mean_c.assign(p, 0.0);
     ctx->live.insert(g);
     *out = g;
@@ -736,6 +737,20 @@ extern "C" int32_t abo_gp_set_params(abo_gp* g, double inv_ls, double scale, dou
     if (!(inv_ls > 0) || !(scale > 0) || !(noise >= 0) || !std::isfinite(inv_ls) || !std::isfinite(scale))
         return abo_fail(ABO_ERR_INVALID, "hyper-parameters must be positive and finite (noise >= 0)");
     g->s = inv_ls; g->scale = scale; g->noise = noise;
+    g->sv.assign(g->d, inv_ls); g->ard = false;
+    for (int a = 0; a < g->p; ++a) g->mean_c[a] = mean_c ? mean_c[a] : 0.0;
+    g->fitted = false;
+    return ABO_OK;
+}
+
+extern "C" int32_t abo_gp_set_params_ard(abo_gp* g, const double* inv_ls, double scale, double noise, const double* mean_c) {
+    if (!g || !inv_ls) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (g->d > ARD_MAXD) return abo_fail(ABO_ERR_INVALID, "ARD length scales are supported for d <= %d", ARD_MAXD);
+    for (int k = 0; k < g->d; ++k)
+        if (!(inv_ls[k] > 0) || !std::isfinite(inv_ls[k])) return abo_fail(ABO_ERR_INVALID, "inverse length scales must be positive and finite");
+    if (!(scale > 0) || !(noise >= 0) || !std::isfinite(scale)) return abo_fail(ABO_ERR_INVALID, "hyper-parameters must be positive and finite (noise >= 0)");
+    g->sv.assign(inv_ls, inv_ls + g->d);
+    g->s = inv_ls[0]; g->scale = scale; g->noise = noise; g->ard = true;
     for (int a = 0; a < g->p; ++a) g->mean_c[a] = mean_c ? mean_c[a] : 0.0;
     g->fitted = false;
     return ABO_OK;
@@ -744,6 +759,7 @@ extern "C" int32_t abo_gp_set_params(abo_gp* g, double inv_ls, double scale, dou
 static KSpec gp_spec(const abo_gp* g) {
     KSpec k;
     k.kind = g->kind; k.d = g->d; k.p = g->p; k.s = g->s; k.scale = g->scale; k.noise = g->noise;
+    for (int q = 0; q < ARD_MAXD; ++q) k.sv[q] = (q < g->d && q < (int)g->sv.size()) ? g->sv[q] : g->s;
     return k;
 }
 
@@ -771,7 +787,7 @@ extern "C" int32_t abo_gp_fit(abo_gp* g, const double* X, const double* y, int64
     CU(cudaMemcpyAsync(g->dMeanC, g->mean_c.data(), sizeof(double) * g->p, cudaMemcpyHostToDevice, st));
     {
         int64_t tot = g->ldx * g->d;
-        scale_transpose_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(dXraw, g->dXsT, n, g->d, g->ldx, g->s);
+        scale_transpose_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(dXraw, g->dXsT, n, g->d, g->ldx, gp_spec(g));
         KL(c);
         fill_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(g->dDelta, Npad, 0.0);
         KL(c);
@@ -779,7 +795,7 @@ extern "C" int32_t abo_gp_fit(abo_gp* g, const double* X, const double* y, int64
         KL(c);
     }
     const int T = (int)(Npad / NB);
-    KmatBatch bt{nullptr, nullptr, 0, 0};
+    KmatBatch bt{nullptr, nullptr, 0, 0, 0};
     launch_kmat(gp_spec(g), g->dXsT, g->ldx, N, g->dL, g->ld, bt, T, 1, st);
     KL(c);
 
@@ -970,7 +986,8 @@ int sweep_device(abo_gp* g, const double* dXc, int64_t m, int bo, int acq, const
     a.p0 = params ? params[0] : 0.0;
     a.p1 = (params && acq != ACQ_UCB && acq >= 0) ? params[1] : 0.0;
     a.mean_c = g->mean_c[bo];
-    a.kss = (bo == 0) ? g->scale : -2.0 * g->s * g->s * g->scale * phi_prime0(g->kind);
+    const double sb_ = (bo > 0 && bo - 1 < (int)g->sv.size() && g->d <= ARD_MAXD) ? g->sv[bo - 1] : g->s;
+    a.kss = (bo == 0) ? g->scale : -2.0 * sb_ * sb_ * g->scale * phi_prime0(g->kind);
     for (int64_t c0 = 0; c0 < m; c0 += mc) {
         const int64_t mvalid = std::min(mc, m - c0);
         const int64_t mc_eff = (mvalid + NB - 1) / NB * NB;

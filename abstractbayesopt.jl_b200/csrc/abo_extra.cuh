@@ -16,6 +16,7 @@ using namespace abo;
 static KSpec spec_of(const abo_gp* g) {
     KSpec k;
     k.kind = g->kind; k.d = g->d; k.p = g->p; k.s = g->s; k.scale = g->scale; k.noise = g->noise;
+    for (int q = 0; q < ARD_MAXD; ++q) k.sv[q] = (q < g->d && q < (int)g->sv.size()) ? g->sv[q] : g->s;
     return k;
 }
 
@@ -181,7 +182,7 @@ static int append_block(abo_gp* g, const double* x, const double* y, int64_t* in
     if (g->n + 1 > g->ldx) { if ((rc = grow_points(g))) return rc; }
     CU(cudaMemcpyAsync(dsmall, small.data(), sizeof(double) * nsmall, cudaMemcpyHostToDevice, st));
     append_block_commit_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(g->dL, g->dLinv, g->ld, N, p, W, Z, WB, dsmall, g->dDelta,
-                                                                           g->dBeta, g->dAlpha, g->dXsT, g->ldx, g->n, d, g->s);
+                                                                           g->dBeta, g->dAlpha, g->dXsT, g->ldx, g->n, d, spec_of(g));
     KL(c);
     CU(cudaStreamSynchronize(st));
     g->n += 1; g->N += p;
@@ -240,7 +241,7 @@ extern "C" int32_t abo_gp_append(abo_gp* g, const double* x, const double* y, in
     }
     if (n + 1 > g->ldx) { if ((rc = grow_points(g))) return rc; }
     append_commit_kernel<<<1, 1024, 0, st>>>(g->dL, g->dLinv, g->ld, n, w, r, l, y[0] - g->mean_c[0], g->dDelta, g->dBeta,
-                                             g->dAlpha, g->dXsT, g->ldx, dx, g->d, g->s);
+                                             g->dAlpha, g->dXsT, g->ldx, dx, g->d, spec_of(g));
     KL(c);
     CU(cudaStreamSynchronize(st));
     g->n = n + 1; g->N = n + 1;
@@ -253,9 +254,11 @@ extern "C" int32_t abo_gp_append(abo_gp* g, const double* x, const double* y, in
 //   beta_b, alpha_b -> Cinv_b = Linv_b^T Linv_b (DMMA, structurally-zero k skipped) ->
 //   fused reduction  sum (Cinv - alpha alpha^T) .* dK/dtheta  with dK recomputed from X.
 // ------------------------------------------------------------------------------------------
-extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, int64_t n, const double* logparams,
-                                  int64_t R, double* nlml, double* grad, int32_t* info) {
+static int nlml_batch_impl(abo_gp* g, const double* X, const double* y, int64_t n, const double* logparams,
+                           int64_t R, double* nlml, double* grad, int32_t* info, bool ard) {
     if (!g || !X || !y || !logparams || !nlml) return abo_fail(ABO_ERR_INVALID, "null argument");
+    if (ard && (g->p != 1 || g->d > ARD_MAXD))
+        return abo_fail(ABO_ERR_INVALID, "the ARD marginal likelihood is implemented for StandardGP (p = 1) with d <= %d", ARD_MAXD);
     if (n < 1) return abo_fail(ABO_ERR_DIM, "need at least one observation");
     if (R <= 0) return ABO_OK;
     if (!g->ctx) return abo_fail(ABO_ERR_INVALID, "the context of this handle has been destroyed");
@@ -263,6 +266,8 @@ extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, i
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const int d = g->d, p = g->p;
+    const int np_ = ard ? d + 1 : 2;                      // parameters (and gradient components) per restart
+    const int ns_ = ard ? d : 1;                          // inverse length scales per restart
     const int64_t N = n * p, Npad = (N + NB - 1) / NB * NB, ldx = (n + NB - 1) / NB * NB;
     const int T = (int)(Npad / NB);
     const size_t mat = sizeof(double) * (size_t)Npad * Npad;
@@ -277,40 +282,40 @@ extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, i
     if ((rc = ws_get(c, WS_NLML_LINV, mat * Rc, (void**)&Linv))) return rc;
     if ((rc = ws_get(c, WS_NLML_W, mat * Rc, (void**)&W))) return rc;
     if ((rc = ws_get(c, WS_NLML_X, sizeof(double) * (size_t)Rc * ldx * d, (void**)&Xb))) return rc;
-    // vec: delta[Rc][Npad] | beta | alpha | out[Rc][3]
-    if ((rc = ws_get(c, WS_NLML_VEC, sizeof(double) * (size_t)Rc * (3 * Npad + 4), (void**)&vec))) return rc;
-    // par: s[Rc] | scale[Rc] | tile partials [Rc][T*T][2]
-    if ((rc = ws_get(c, WS_NLML_PAR, sizeof(double) * (size_t)Rc * (2 + 2 * (size_t)T * T), (void**)&par))) return rc;
+    // vec: delta[Rc][Npad] | beta | alpha | out[Rc][1 + np]
+    if ((rc = ws_get(c, WS_NLML_VEC, sizeof(double) * (size_t)Rc * (3 * Npad + 2 + np_), (void**)&vec))) return rc;
+    // par: s[Rc][ns] | scale[Rc] | tile partials [Rc][T*T][np]
+    if ((rc = ws_get(c, WS_NLML_PAR, sizeof(double) * (size_t)Rc * (ns_ + 1 + np_ * (size_t)T * T), (void**)&par))) return rc;
     if ((rc = ws_get(c, WS_DINV, sizeof(double) * (size_t)Rc * T * NB * NB, (void**)&Dinv))) return rc;
     if ((rc = ws_get(c, WS_INFO, sizeof(int) * std::max<int64_t>(16, Rc), (void**)&dinfo))) return rc;
     if ((rc = ws_get(c, WS_STAGE_X, sizeof(double) * (size_t)n * d, (void**)&dXraw))) return rc;
     if ((rc = ws_get(c, WS_STAGE_Y, sizeof(double) * (size_t)(N + p), (void**)&dYraw))) return rc;
     double *delta = vec, *beta = vec + Rc * Npad, *alpha = beta + Rc * Npad, *out = alpha + Rc * Npad;
-    double *sb = par, *scb = par + Rc, *tpart = par + 2 * Rc;
+    double *sb = par, *scb = par + Rc * ns_, *tpart = par + Rc * (ns_ + 1);
     CU(cudaMemcpyAsync(dXraw, X, sizeof(double) * n * d, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(dYraw, y, sizeof(double) * N, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(dYraw + N, g->mean_c.data(), sizeof(double) * p, cudaMemcpyHostToDevice, st));
-    std::vector<double> hs(Rc), hsc(Rc), hout(3 * Rc);
+    std::vector<double> hs(Rc * ns_), hsc(Rc), hout((1 + np_) * Rc);
     std::vector<int> hinfo(Rc);
     KSpec spec = spec_of(g);
     for (int64_t r0 = 0; r0 < R; r0 += Rc) {
         const int nb = (int)std::min<int64_t>(Rc, R - r0);
         for (int b = 0; b < nb; ++b) {
-            hs[b] = std::exp(-logparams[2 * (r0 + b)]);           // s = 1 / l
-            hsc[b] = std::exp(logparams[2 * (r0 + b) + 1]);
+            for (int k = 0; k < ns_; ++k) hs[b * ns_ + k] = std::exp(-logparams[np_ * (r0 + b) + k]);   // s = 1 / l
+            hsc[b] = std::exp(logparams[np_ * (r0 + b) + np_ - 1]);
         }
-        CU(cudaMemcpyAsync(sb, hs.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(sb, hs.data(), sizeof(double) * nb * ns_, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(scb, hsc.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(dinfo, 0, sizeof(int) * nb, st));
         CU(cudaMemsetAsync(delta, 0, sizeof(double) * (size_t)nb * Npad, st));
         {
             int64_t tot = ldx * d;
-            scale_transpose_batched_kernel<<<dim3((unsigned)((tot + 255) / 256), nb), 256, 0, st>>>(dXraw, Xb, n, d, ldx, sb);
+            scale_transpose_batched_kernel<<<dim3((unsigned)((tot + 255) / 256), nb), 256, 0, st>>>(dXraw, Xb, n, d, ldx, sb, ard ? 1 : 0);
             KL(c);
             delta_batched_kernel<<<dim3((unsigned)((N + 255) / 256), nb), 256, 0, st>>>(dYraw, dYraw + N, n, p, delta, Npad);
             KL(c);
         }
-        KmatBatch bt{sb, scb, ldx * d, Npad * Npad};
+        KmatBatch bt{sb, scb, ldx * d, Npad * Npad, ard ? 1 : 0};
         launch_kmat(spec, Xb, ldx, N, Kb, Npad, bt, T, nb, st);
         KL(c);
         if ((rc = potrf_blocked(c, Kb, Npad, Npad, Npad * Npad, Dinv, (int64_t)T * NB * NB, dinfo, nb))) return rc;
@@ -324,19 +329,27 @@ extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, i
             if (Npad >= ws_min_n()) CU((launch_gemm_ws<MC, MC>(q, nb, st, c->sms)));
             else CU((launch_gemm<MC, MC, EPI_STORE>(q, nb, st)));
             KL(c);
-            launch_nlml_grad(spec, bt, Xb, ldx, N, W, Npad, Npad * Npad, alpha, Npad, tpart, T, nb, st);
+            if (ard) {
+                const dim3 grid(T, T, nb);
+                if (d <= 8) nlml_grad_ard_kernel<8><<<grid, 256, 0, st>>>(spec, bt, Xb, ldx, N, W, Npad, Npad * Npad, alpha, Npad, tpart);
+                else if (d <= 20) nlml_grad_ard_kernel<20><<<grid, 256, 0, st>>>(spec, bt, Xb, ldx, N, W, Npad, Npad * Npad, alpha, Npad, tpart);
+                else nlml_grad_ard_kernel<32><<<grid, 256, 0, st>>>(spec, bt, Xb, ldx, N, W, Npad, Npad * Npad, alpha, Npad, tpart);
+            } else {
+                launch_nlml_grad(spec, bt, Xb, ldx, N, W, Npad, Npad * Npad, alpha, Npad, tpart, T, nb, st);
+            }
             KL(c);
         } else {
-            CU(cudaMemsetAsync(tpart, 0, sizeof(double) * (size_t)nb * T * T * 2, st));
+            CU(cudaMemsetAsync(tpart, 0, sizeof(double) * (size_t)nb * T * T * np_, st));
         }
-        nlml_finish_kernel<<<nb, 256, 0, st>>>(Kb, Npad, Npad * Npad, N, beta, Npad, tpart, T * T, dinfo, out);
+        if (ard) nlml_finish_ard_kernel<<<nb, 256, 0, st>>>(Kb, Npad, Npad * Npad, N, beta, Npad, tpart, T * T, np_, dinfo, out);
+        else nlml_finish_kernel<<<nb, 256, 0, st>>>(Kb, Npad, Npad * Npad, N, beta, Npad, tpart, T * T, dinfo, out);
         KL(c);
-        CU(cudaMemcpyAsync(hout.data(), out, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hout.data(), out, sizeof(double) * (1 + np_) * nb, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(hinfo.data(), dinfo, sizeof(int) * nb, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         for (int b = 0; b < nb; ++b) {
-            nlml[r0 + b] = hout[3 * b];
-            if (grad) { grad[2 * (r0 + b)] = hout[3 * b + 1]; grad[2 * (r0 + b) + 1] = hout[3 * b + 2]; }
+            nlml[r0 + b] = hout[(1 + np_) * b];
+            if (grad) for (int k = 0; k < np_; ++k) grad[np_ * (r0 + b) + k] = hout[(1 + np_) * b + 1 + k];
             if (info) info[r0 + b] = hinfo[b];
         }
     }
@@ -344,4 +357,13 @@ extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, i
         ws_release(c, WS_NLML_K); ws_release(c, WS_NLML_LINV); ws_release(c, WS_NLML_W);
     }
     return ABO_OK;
+}
+
+extern "C" int32_t abo_nlml_batch(abo_gp* g, const double* X, const double* y, int64_t n, const double* logparams,
+                                  int64_t R, double* nlml, double* grad, int32_t* info) {
+    return nlml_batch_impl(g, X, y, n, logparams, R, nlml, grad, info, false);
+}
+extern "C" int32_t abo_nlml_batch_ard(abo_gp* g, const double* X, const double* y, int64_t n, const double* logparams,
+                                      int64_t R, double* nlml, double* grad, int32_t* info) {
+    return nlml_batch_impl(g, X, y, n, logparams, R, nlml, grad, info, true);
 }

@@ -68,6 +68,8 @@ struct abo_gp {
     abo_ctx* ctx = nullptr;
     int kind = 0, d = 1, p = 1;
     double s = 1.0, scale = 1.0, noise = 0.0;
+    std::vector<double> sv;               // per-dimension inverse length scales (ARD); all equal to s when isotropic
+    bool ard = false;
     std::vector<double> mean_c;
     int64_t n = 0, N = 0, Npad = 0;      // points, system size n*p, padded to 128
     int64_t cap_pad = 0, ld = 0, ldx = 0;

@@ -145,7 +145,7 @@ extern "C" int32_t abo_gp_sync(abo_gp* g, int32_t root) {
     CU(cudaSetDevice(c->device));
     // ---- header: ALWAYS broadcast, with the root's own status in it (h[11]) — an un-fitted root must not return
     //      before the collective its peers are already waiting in
-    const int HN = 16 + 64;
+    const int HN = 16 + 64 + 32;                       // scalars | prior means (p <= 64) | per-dimension inverse length scales (ARD)
     std::vector<double> h(HN, 0.0);
     if (c->rank == root) {
         int st = ABO_OK;
@@ -156,6 +156,8 @@ extern "C" int32_t abo_gp_sync(abo_gp* g, int32_t root) {
             h[0] = (double)g->n; h[1] = (double)g->N; h[2] = (double)g->Npad; h[3] = (double)g->ldx; h[4] = g->kind;
             h[5] = g->d; h[6] = g->p; h[7] = g->s; h[8] = g->scale; h[9] = g->noise; h[10] = (double)g->cap_pad;
             for (int a = 0; a < g->p; ++a) h[16 + a] = g->mean_c[a];
+            h[12] = g->ard ? 1.0 : 0.0;
+            for (int k = 0; k < g->d && k < 32; ++k) h[80 + k] = g->sv[k];
         }
     }
     int rc = bcast_doubles(c, h, root);
@@ -172,6 +174,9 @@ extern "C" int32_t abo_gp_sync(abo_gp* g, int32_t root) {
         } else {
             g->kind = (int)h[4]; g->s = h[7]; g->scale = h[8]; g->noise = h[9];
             for (int a = 0; a < g->p; ++a) g->mean_c[a] = h[16 + a];
+            g->ard = h[12] != 0.0;
+            g->sv.assign(g->d, g->s);
+            for (int k = 0; k < g->d && k < 32; ++k) g->sv[k] = h[80 + k];
             const int64_t cap = (int64_t)h[10], ldx = (int64_t)h[3];
             g->fitted = false;
             if (cap != g->cap_pad || ldx != g->ldx || gp_shared(g)) mine = gp_alloc(g, cap, ldx);

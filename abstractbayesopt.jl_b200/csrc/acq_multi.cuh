@@ -61,11 +61,12 @@ __global__ void __launch_bounds__(128) acq_multi_finish_kernel(KSpec spec, Multi
     }
     double ph, dph, ddph;
     phi_eval(spec.kind, 0.0, ph, dph, ddph);
-    const double kvv = spec.scale * ph, kgg = -2.0 * spec.s * spec.s * spec.scale * dph;   // prior variances (off-diagonals vanish at D = 0)
+    const double kvv = spec.scale * ph;                   // prior variances (off-diagonals vanish at D = 0); gradient output b: -2 s_b^2 sig2 phi'(0)
     auto sigma = [&](int b, int b2) {                     // posterior covariance of outputs b >= b2 at this point
         double g = 0.0;
         const int pair = b * (b + 1) / 2 + b2;
         for (int ch = 0; ch < nchunks; ++ch) g += part[((int64_t)ch * npair + pair) * mc + c];
+        const double kgg = (b > 0) ? -2.0 * spec.sk(b - 1) * spec.sk(b - 1) * spec.scale * dph : 0.0;
         return ((b == b2) ? (b == 0 ? kvv : kgg) : 0.0) - g + ((b == b2) ? JITTER : 0.0);
     };
     double total = 0.0;

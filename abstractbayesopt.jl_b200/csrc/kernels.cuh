@@ -23,9 +23,12 @@ constexpr double JITTER = 1e-18;        // AbstractGPs default_σ² (StandardGP.
 enum KernelId { K_SE = 0, K_M52 = 1, K_M72 = 2, K_AM52 = 3, K_AM72 = 4, K_ADM52 = 5, K_ADM72 = 6 };
 enum AcqId { ACQ_EI = 0, ACQ_PI = 1, ACQ_UCB = 2 };
 
+constexpr int ARD_MAXD = 32;
 struct KSpec {
     int kind, d, p;
-    double s, scale, noise;
+    double s, scale, noise;      // s: the isotropic ScaleTransform 1/l (also what the d > 32 kernels use)
+    double sv[ARD_MAXD];         // per-dimension inverse length scales s_k = 1/l_k (ARD; all equal to s for an isotropic kernel)
+    __host__ __device__ __forceinline__ double sk(int k) const { return d <= ARD_MAXD ? sv[k] : s; }
 };
 
 // phi(u), phi'(u), phi''(u), u = squared scaled distance.
@@ -57,26 +60,27 @@ __device__ __forceinline__ void phi_eval(int kind, double u, double& p, double& 
 }
 
 // gradKernel entry (src/surrogates/GradientGP.jl:573-606) in closed form; D = s*(x - y).
-//   (0,0) sig2 phi ; (a,0) 2 s sig2 phi' D_a ; (0,b) -2 s sig2 phi' D_b ;
-//   (a,b) -sig2 [ 4 s^2 phi'' D_a D_b + 2 s^2 phi' delta_ab ]
+//   (0,0) sig2 phi ; (a,0) 2 s_a sig2 phi' D_a ; (0,b) -2 s_b sig2 phi' D_b ;
+//   (a,b) -sig2 [ 4 s_a s_b phi'' D_a D_b + 2 s_a^2 phi' delta_ab ]        (s_a = s for an isotropic kernel)
 __device__ __forceinline__ double gk_entry(const KSpec& ks, double p, double dp, double ddp, int a, int b,
                                            double Da, double Db) {
     if (a == 0 && b == 0) return ks.scale * p;
-    if (b == 0) return 2 * ks.s * ks.scale * dp * Da;
-    if (a == 0) return -2 * ks.s * ks.scale * dp * Db;
-    return -ks.scale * (4 * ks.s * ks.s * ddp * Da * Db + (a == b ? 2 * ks.s * ks.s * dp : 0.0));
+    if (b == 0) return 2 * ks.sk(a - 1) * ks.scale * dp * Da;
+    if (a == 0) return -2 * ks.sk(b - 1) * ks.scale * dp * Db;
+    const double sa = ks.sk(a - 1), sb = ks.sk(b - 1);
+    return -ks.scale * (4 * sa * sb * ddp * Da * Db + (a == b ? 2 * sa * sa * dp : 0.0));
 }
 
 // ------------------------------------------------------------------------------------------
 // coordinates:  XsT[k*ldx + i] = s * X[i*d + k]
 // ------------------------------------------------------------------------------------------
 __global__ void scale_transpose_kernel(const double* __restrict__ X, double* __restrict__ XsT, int64_t n,
-                                       int d, int64_t ldx, double s) {
+                                       int d, int64_t ldx, KSpec spec) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= ldx * d) return;
     int k = (int)(t / ldx);
     int64_t i = t % ldx;
-    XsT[t] = (i < n) ? s * X[i * d + k] : 0.0;
+    XsT[t] = (i < n) ? spec.sk(k) * X[i * d + k] : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -85,18 +89,31 @@ __global__ void scale_transpose_kernel(const double* __restrict__ X, double* __r
 // Batched form (NLML restarts): per-batch KSpec parameters come from arrays.
 // ------------------------------------------------------------------------------------------
 struct KmatBatch {
-    const double* s;       // per batch inverse lengthscale (nullptr: use spec.s)
+    const double* s;       // per batch inverse lengthscale (nullptr: use spec.s); with ARD: [batch][d] (see `ard`)
     const double* scale;   // per batch sigma^2
     int64_t strideX;       // XsT stride per batch
     int64_t strideK;
+    int ard;               // 1: s holds d inverse length scales per batch
 };
+// hyper-parameters of batch entry z into the by-value KSpec copy of a kernel
+__device__ __forceinline__ void apply_batch(KSpec& spec, const KmatBatch& bt, int z) {
+    if (!bt.s) return;
+    spec.scale = bt.scale[z];
+    if (bt.ard) {
+        for (int k = 0; k < spec.d && k < ARD_MAXD; ++k) spec.sv[k] = bt.s[(int64_t)z * spec.d + k];
+        spec.s = spec.sv[0];
+    } else {
+        spec.s = bt.s[z];
+        for (int k = 0; k < ARD_MAXD; ++k) spec.sv[k] = spec.s;
+    }
+}
 
 __global__ void __launch_bounds__(256) kmat_kernel(KSpec spec, const double* __restrict__ XsT, int64_t ldx,
                                                    int64_t N, double* __restrict__ Kmat, int64_t ld,
                                                    KmatBatch bt) {
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (bj > bi) return;
-    if (bt.s) { spec.s = bt.s[blockIdx.z]; spec.scale = bt.scale[blockIdx.z]; }
+    apply_batch(spec, bt, blockIdx.z);
     const double* X = XsT + (int64_t)blockIdx.z * bt.strideX;
     double* Kb = Kmat + (int64_t)blockIdx.z * bt.strideK;
     const int c = threadIdx.x & 127;
@@ -137,7 +154,7 @@ __global__ void __launch_bounds__(256) kmat_p1_kernel(KSpec spec, const double* 
                                                       double* __restrict__ Kmat, int64_t ld, KmatBatch bt) {
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (bj > bi) return;
-    if (bt.s) { spec.s = bt.s[blockIdx.z]; spec.scale = bt.scale[blockIdx.z]; }
+    apply_batch(spec, bt, blockIdx.z);
     const double* X = XsT + (int64_t)blockIdx.z * bt.strideX;
     double* Kb = Kmat + (int64_t)blockIdx.z * bt.strideK;
     __shared__ double sxi[DT][NB];
@@ -610,7 +627,7 @@ __global__ void __launch_bounds__(128) ks_build_kernel(KSpec spec, const double*
     for (int e = tid; e < KS_CB * DT; e += 128) {
         int c = e / DT, k = e - c * DT;
         int64_t gc = c_begin + cb0 + c;
-        sc[c][k] = (k < spec.d && gc < m_total) ? spec.s * Xc[gc * spec.d + k] : 0.0;
+        sc[c][k] = (k < spec.d && gc < m_total) ? spec.sk(k) * Xc[gc * spec.d + k] : 0.0;
     }
     double x[DT];
 #pragma unroll
@@ -794,7 +811,7 @@ __global__ void kvec_kernel(KSpec spec, const double* __restrict__ XsT, int64_t 
     if (i >= n) { kv[i] = 0.0; return; }
     double u = 0.0;
     for (int k = 0; k < spec.d; ++k) {
-        double df = XsT[k * ldx + i] - spec.s * xnew[k];
+        double df = XsT[k * ldx + i] - spec.sk(k) * xnew[k];
         u = fma(df, df, u);
     }
     double p, dp, ddp;
@@ -822,7 +839,7 @@ __global__ void __launch_bounds__(1024) append_commit_kernel(double* __restrict_
                                                              const double* __restrict__ r, double l, double delta_n,
                                                              double* __restrict__ delta, double* __restrict__ beta,
                                                              double* __restrict__ alpha, double* __restrict__ XsT,
-                                                             int64_t ldx, const double* __restrict__ xnew, int d, double s) {
+                                                             int64_t ldx, const double* __restrict__ xnew, int d, KSpec spec) {
     __shared__ double sh[1024];
     __shared__ double s_beta;
     const double linv = 1.0 / l;
@@ -851,7 +868,7 @@ __global__ void __launch_bounds__(1024) append_commit_kernel(double* __restrict_
     __syncthreads();
     const double bn = s_beta;
     for (int64_t j = threadIdx.x; j < n; j += 1024) alpha[j] = fma(Linv[n * ld + j], bn, alpha[j]);
-    for (int k = threadIdx.x; k < d; k += 1024) XsT[k * ldx + n] = s * xnew[k];
+    for (int k = threadIdx.x; k < d; k += 1024) XsT[k * ldx + n] = spec.sk(k) * xnew[k];
 }
 // ---- skinny triangular products for a handful of right-hand sides (block append): bandwidth-bound passes over
 //      the triangle instead of 128-wide padded GEMM tiles.  RHS columns are processed 8 at a time (blockIdx.y).
@@ -969,7 +986,7 @@ __global__ void __launch_bounds__(256) append_block_commit_kernel(double* __rest
                                                                   const double* __restrict__ small, double* __restrict__ delta,
                                                                   double* __restrict__ beta, double* __restrict__ alpha,
                                                                   double* __restrict__ XsT, int64_t ldx, int64_t npts, int d,
-                                                                  double s) {
+                                                                  KSpec spec) {
     const double* LS = small;
     const double* LSinv = small + p * p;
     const double* bnew = LSinv + p * p;
@@ -994,7 +1011,7 @@ __global__ void __launch_bounds__(256) append_block_commit_kernel(double* __rest
             if (b <= a) { L[(N + a) * ld + N + b] = LS[e]; Linv[(N + a) * ld + N + b] = LSinv[e]; }
         }
         for (int a = threadIdx.x; a < p; a += 256) { alpha[N + a] = gamma[a]; beta[N + a] = bnew[a]; delta[N + a] = dnew[a]; }
-        for (int q = threadIdx.x; q < d; q += 256) XsT[q * ldx + npts] = s * x[q];
+        for (int q = threadIdx.x; q < d; q += 256) XsT[q * ldx + npts] = spec.sk(q) * x[q];
     }
 }
 // grow a padded lower-triangular matrix: copy the old Npad x Npad block, identity in the new part
@@ -1011,12 +1028,13 @@ __global__ void grow_matrix_kernel(const double* __restrict__ src, int64_t old_p
 // ------------------------------------------------------------------------------------------
 // per-batch scaled coordinates: XsT[b][k*ldx + i] = s_b * X[i*d + k]
 __global__ void scale_transpose_batched_kernel(const double* __restrict__ X, double* __restrict__ XsT, int64_t n, int d,
-                                               int64_t ldx, const double* __restrict__ sb) {
+                                               int64_t ldx, const double* __restrict__ sb, int ard) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= ldx * d) return;
     int k = (int)(t / ldx);
     int64_t i = t % ldx;
-    XsT[(int64_t)blockIdx.y * ldx * d + t] = (i < n) ? sb[blockIdx.y] * X[i * d + k] : 0.0;
+    const double s = ard ? sb[(int64_t)blockIdx.y * d + k] : sb[blockIdx.y];
+    XsT[(int64_t)blockIdx.y * ldx * d + t] = (i < n) ? s * X[i * d + k] : 0.0;
 }
 // d/dlog(l) of a gradKernel entry.  s = 1/l, u = s^2 r^2, D = s * Delta:
 //   ds = -s, du = -2u, dD = -D.  uphi3 = u * (third derivative of phi at u).
@@ -1053,7 +1071,7 @@ __global__ void __launch_bounds__(256) nlml_grad_tile_kernel(KSpec spec, KmatBat
     const int T = gridDim.x;
     double g0 = 0.0, g1 = 0.0;
     if (bj <= bi) {
-        spec.s = bt.s[blockIdx.z]; spec.scale = bt.scale[blockIdx.z];
+        apply_batch(spec, bt, blockIdx.z);
         const double* X = XsT + (int64_t)blockIdx.z * bt.strideX;
         const double* Cb = Cinv + (int64_t)blockIdx.z * strideC;
         const double* al = alpha + (int64_t)blockIdx.z * strideV;
@@ -1108,7 +1126,7 @@ __global__ void __launch_bounds__(256, 2) nlml_grad_p1_kernel(KSpec spec, KmatBa
     const int tid = threadIdx.x;
     double g0 = 0.0, g1 = 0.0;
     if (bj <= bi) {
-        spec.s = bt.s[blockIdx.z]; spec.scale = bt.scale[blockIdx.z];
+        apply_batch(spec, bt, blockIdx.z);
         const double* X = XsT + (int64_t)blockIdx.z * bt.strideX;
         const double* Cb = Cinv + (int64_t)blockIdx.z * strideC;
         const double* al = alpha + (int64_t)blockIdx.z * strideV;
@@ -1179,6 +1197,88 @@ __global__ void __launch_bounds__(256, 2) nlml_grad_p1_kernel(KSpec spec, KmatBa
     if (tid == 0) {
         double* o = part + ((int64_t)blockIdx.z * T * T + (int64_t)bi * T + bj) * 2;
         o[0] = sh[0][0]; o[1] = sh[1][0];
+    }
+}
+
+// ARD (per-dimension length scales), scalar GP: per lower tile the d + 1 partial sums
+//   part[b][tile][k]  = sum_ij M_ij dK_ij/dlog l_k = sum_ij M_ij (-2 sig2 phi'(u_ij) D_ij,k^2)      k < d
+//   part[b][tile][d]  = sum_ij M_ij K_ij                                                           (d/dlog sig2)
+// (u = sum_k D_k^2, D_k = s_k (x_ik - x_jk): du/dlog l_k = -2 D_k^2), M = Cinv - alpha alpha^T over the full symmetric matrix.
+template <int DT>
+__global__ void __launch_bounds__(256) nlml_grad_ard_kernel(KSpec spec, KmatBatch bt, const double* __restrict__ XsT, int64_t ldx,
+                                                            int64_t N, const double* __restrict__ Cinv, int64_t ld, int64_t strideC,
+                                                            const double* __restrict__ alpha, int64_t strideV,
+                                                            double* __restrict__ part) {
+    __shared__ double sh[8][DT + 1];
+    const int bi = blockIdx.y, bj = blockIdx.x, T = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = spec.d;
+    double g[DT + 1];
+#pragma unroll
+    for (int k = 0; k <= DT; ++k) g[k] = 0.0;
+    if (bj <= bi) {
+        apply_batch(spec, bt, blockIdx.z);
+        const double* X = XsT + (int64_t)blockIdx.z * bt.strideX;
+        const double* Cb = Cinv + (int64_t)blockIdx.z * strideC;
+        const double* al = alpha + (int64_t)blockIdx.z * strideV;
+        const int64_t gc = (int64_t)bj * NB + (tid & 127);
+        double xj[DT];
+#pragma unroll
+        for (int k = 0; k < DT; ++k) xj[k] = (k < d && gc < N) ? X[k * ldx + gc] : 0.0;
+        const double alc = gc < N ? al[gc] : 0.0;
+        for (int r = tid >> 7; r < NB; r += 2) {
+            const int64_t gr = (int64_t)bi * NB + r;
+            if (gr >= N || gc >= N || gc > gr) continue;
+            double df2[DT], u = 0.0;
+#pragma unroll
+            for (int k = 0; k < DT; ++k) { const double df = (k < d ? X[k * ldx + gr] : 0.0) - xj[k]; df2[k] = df * df; u += df2[k]; }
+            double ph, dph, ddph;
+            phi_eval(spec.kind, u, ph, dph, ddph);
+            const double m = (Cb[gr * ld + gc] - al[gr] * alc) * (gr == gc ? 1.0 : 2.0);
+            const double w = -2.0 * spec.scale * dph * m;
+#pragma unroll
+            for (int k = 0; k < DT; ++k) g[k] = fma(w, df2[k], g[k]);
+            g[DT] = fma(m, spec.scale * ph, g[DT]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k <= DT; ++k) {
+        double v = g[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid <= d) {
+        const int k = (tid == d) ? DT : tid;
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += sh[w][k];
+        part[((int64_t)blockIdx.z * T * T + (int64_t)bi * T + bj) * (d + 1) + tid] = v;
+    }
+}
+// one block per batch entry: out[b] = { nlml, g_1 .. g_ng }
+__global__ void __launch_bounds__(256) nlml_finish_ard_kernel(const double* __restrict__ L, int64_t ld, int64_t strideM, int64_t N,
+                                                              const double* __restrict__ beta, int64_t strideV,
+                                                              const double* __restrict__ part, int ntile, int ng,
+                                                              const int* __restrict__ info, double* __restrict__ out) {
+    __shared__ double sh[2][256];
+    const double* Lb = L + (int64_t)blockIdx.x * strideM;
+    const double* bb = beta + (int64_t)blockIdx.x * strideV;
+    double* o = out + (int64_t)blockIdx.x * (1 + ng);
+    const int tid = threadIdx.x;
+    double ld_ = 0.0, qq = 0.0;
+    for (int64_t i = tid; i < N; i += 256) { ld_ += log(Lb[i * ld + i]); qq = fma(bb[i], bb[i], qq); }
+    sh[0][tid] = ld_; sh[1][tid] = qq;
+    __syncthreads();
+    for (int s_ = 128; s_ > 0; s_ >>= 1) {
+        if (tid < s_) { sh[0][tid] += sh[0][tid + s_]; sh[1][tid] += sh[1][tid + s_]; }
+        __syncthreads();
+    }
+    const bool bad = info[blockIdx.x] != 0;
+    if (tid == 0) o[0] = bad ? CUDART_INF : 0.5 * ((double)N * 1.8378770664093454836 + 2.0 * sh[0][0] + sh[1][0]);
+    if (tid < ng) {
+        double v = 0.0;
+        for (int t = 0; t < ntile; ++t) v += part[((int64_t)blockIdx.x * ntile + t) * ng + tid];
+        o[1 + tid] = bad ? CUDART_NAN : 0.5 * v;
     }
 }
 
@@ -1407,7 +1507,7 @@ __global__ void __launch_bounds__(128) acq_grad_partial_kernel(KSpec spec, const
     if (i < npts && c < m) {
         double u = 0.0;
         for (int k = 0; k < d; ++k) {
-            const double df = XsT[k * ldx + i] - spec.s * Xc[(int64_t)c * d + k];
+            const double df = XsT[k * ldx + i] - spec.sk(k) * Xc[(int64_t)c * d + k];
             u = fma(df, df, u);
         }
         double ph, dph, ddph;
@@ -1415,11 +1515,11 @@ __global__ void __launch_bounds__(128) acq_grad_partial_kernel(KSpec spec, const
         for (int a = 0; a < p; ++a) {
             const int64_t idx = i * p + a;
             const double al = alpha[idx], zz = Z[idx * mpad + c];
-            const double Da = (a == 0) ? 0.0 : XsT[(a - 1) * ldx + i] - spec.s * Xc[(int64_t)c * d + a - 1];
+            const double Da = (a == 0) ? 0.0 : XsT[(a - 1) * ldx + i] - spec.sk(a - 1) * Xc[(int64_t)c * d + a - 1];
 #pragma unroll
             for (int b = 0; b < AG_MAXD; ++b) {
                 if (b < d) {
-                    const double Db = XsT[b * ldx + i] - spec.s * Xc[(int64_t)c * d + b];
+                    const double Db = XsT[b * ldx + i] - spec.sk(b) * Xc[(int64_t)c * d + b];
                     const double dk = gk_entry(spec, ph, dph, ddph, a, b + 1, Da, Db);
                     gmu[b] = fma(al, dk, gmu[b]);
                     gva[b] = fma(zz, dk, gva[b]);
@@ -1504,7 +1604,7 @@ __global__ void cov_finish_kernel(KSpec spec, const double* __restrict__ Xc, int
     const int64_t c = r % m, c2 = q % m;
     double u = 0.0, Da = 0.0, Db = 0.0;
     for (int k = 0; k < spec.d; ++k) {
-        const double df = spec.s * Xc[c * spec.d + k] - spec.s * Xc[c2 * spec.d + k];
+        const double df = spec.sk(k) * Xc[c * spec.d + k] - spec.sk(k) * Xc[c2 * spec.d + k];
         u = fma(df, df, u);
         if (k == b - 1) Da = df;
         if (k == b2 - 1) Db = df;

@@ -202,7 +202,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int e = tid; e < 128 * DT; e += 256) {
             const int c = e / DT, k = e - c * DT;
             const int64_t gc = c_base + c;
-            sc[e] = (k < d && gc < p.m) ? p.spec.s * p.Xc[gc * d + k] : 0.0;
+            sc[e] = (k < d && gc < p.m) ? p.spec.sk(k) * p.Xc[gc * d + k] : 0.0;
         }
         bar_consumers();
         const int nitems = ((p.dbg & 1) && j > 1) ? 0 : (int)((n + 31) / 32) * 4;

@@ -5,6 +5,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass, replace
 
+import numpy as np
+
 KERNEL_IDS = {
     "SqExponentialKernel": 0, "Matern52Kernel": 1, "Matern72Kernel": 2,
     "ApproxMatern52Kernel": 3, "ApproxMatern72Kernel": 4, "ADMatern52Kernel": 5, "ADMatern72Kernel": 6,
@@ -14,7 +16,7 @@ KERNEL_IDS = {
 @dataclass(frozen=True)
 class Kernel:
     name: str
-    inv_lengthscale: float | None = None   # ScaleTransform s = 1/ℓ (None: no transform yet)
+    inv_lengthscale: float | tuple | None = None   # ScaleTransform s = 1/ℓ (None: no transform yet); a tuple = ARDTransform, s_k = 1/ℓ_k
     scale: float | None = None             # ScaledKernel σ² (None: not scaled yet)
 
     @property
@@ -38,8 +40,11 @@ def ADMatern52Kernel(): return Kernel("ADMatern52Kernel")
 def ADMatern72Kernel(): return Kernel("ADMatern72Kernel")
 
 
-def with_lengthscale(kernel: Kernel, lengthscale: float) -> Kernel:
-    """KernelFunctions.with_lengthscale: base ∘ ScaleTransform(1/ℓ)."""
+def with_lengthscale(kernel: Kernel, lengthscale) -> Kernel:
+    """KernelFunctions.with_lengthscale: base ∘ ScaleTransform(1/ℓ); a vector of length scales gives
+    base ∘ ARDTransform(1 ./ ℓ) (one length scale per input dimension)."""
+    if np.ndim(lengthscale) > 0:
+        return replace(kernel, inv_lengthscale=tuple(1.0 / float(v) for v in np.ravel(lengthscale)))
     return replace(kernel, inv_lengthscale=1.0 / float(lengthscale))
 
 
@@ -48,7 +53,10 @@ def extract_scale_and_lengthscale(kernel: Kernel):
     The lengthscale is 1/s, and the constructor re-applies with_lengthscale(inner, 1/s), i.e.
     the stored s goes through 1/(1/s) exactly as in the reference."""
     scale = 1.0 if kernel.scale is None else kernel.scale
-    ls = None if kernel.inv_lengthscale is None else 1.0 / kernel.inv_lengthscale
+    if isinstance(kernel.inv_lengthscale, tuple):
+        ls = tuple(1.0 / v for v in kernel.inv_lengthscale)
+    else:
+        ls = None if kernel.inv_lengthscale is None else 1.0 / kernel.inv_lengthscale
     return kernel.constructor(), scale, ls
 
 

@@ -46,7 +46,14 @@ class _GpBase(AbstractSurrogate):
 
 
 # -- accessors (StandardGP.jl:261-287, GradientGP.jl:842-870)
-def get_lengthscale(model): return [1.0 / model.kernel.inv_lengthscale]
+def get_lengthscale(model):
+    s = model.kernel.inv_lengthscale
+    return [1.0 / v for v in s] if isinstance(s, tuple) else [1.0 / s]
+
+
+def is_ard(model): return isinstance(model.kernel.inv_lengthscale, tuple)
+
+
 def get_scale(model): return [model.kernel.scale]
 def get_kernel_constructor(model): return model.kernel.constructor()
 
@@ -237,17 +244,19 @@ def nlml_ls(model, log_ls, log_scale, xs, ys):
     return nlml(model, [log_ls, log_scale], xs, ys)
 
 
-def nlml_batch(model, logparams, xs, ys, want_grad=True):
+def nlml_batch(model, logparams, xs, ys, want_grad=True, ard=False):
     """Value and analytic gradient of the NLML for R hyper-parameter vectors in one call
-    (replaces the ForwardDiff.Dual evaluation of bayesian_opt.jl:284)."""
+    (replaces the ForwardDiff.Dual evaluation of bayesian_opt.jl:284).  ard=True: rows are
+    {log l_1 .. log l_d, log sig2} (per-dimension length scales, the extension planned at bayesian_opt.jl:193-194)."""
     X = _as_points(xs)
     n, d = X.shape
     y = _flat_y(model, ys, n)
     ctx = model.ctx or default_context()
     h = GpHandle(ctx, model.kernel.kernel_id, d, model.p)
     try:
-        h.set_params(model.kernel.inv_lengthscale, model.kernel.scale, model.noise_var, np.atleast_1d(model.mean_c))
-        return h.nlml_batch(X, y, logparams, want_grad)
+        isl = model.kernel.inv_lengthscale
+        h.set_params(isl[0] if isinstance(isl, tuple) else isl, model.kernel.scale, model.noise_var, np.atleast_1d(model.mean_c))
+        return h.nlml_batch(X, y, logparams, want_grad, ard=ard)
     finally:
         h.close()
 
@@ -276,7 +285,7 @@ def std_y(model, ys, mu, sd):
 
 def rescale_model(model, sd):
     s = float(np.ravel(sd)[0])
-    ell = get_lengthscale(model)[0]
+    ell = get_lengthscale(model) if is_ard(model) else get_lengthscale(model)[0]
     new_kernel = (get_scale(model)[0] / s ** 2) * with_lengthscale(get_kernel_constructor(model), ell)
     if isinstance(model, GradientGP):
         # quirk mirrored: gradConstMean's inner constructor returns a CustomMean, so the

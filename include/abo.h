@@ -89,6 +89,11 @@ int32_t abo_gp_destroy(abo_gp* gp);
  * output (NULL = ZeroMean).  Invalidates any posterior held by the handle. */
 int32_t abo_gp_set_params(abo_gp* gp, double inv_lengthscale, double scale, double noise_var,
                           const double* mean_c);
+/* ARD: one inverse length scale PER DIMENSION, s_k = 1/l_k (KernelFunctions ARDTransform in place of ScaleTransform).  The
+ * reference lists it as a TODO (src/bayesian_opt.jl:193-194); every entry point below (fit, append, posteriors incl. the
+ * derivative blocks of a GradientGP, acquisitions and their gradients, multi-GPU sync) honours it.  d <= 32. */
+int32_t abo_gp_set_params_ard(abo_gp* gp, const double* inv_lengthscales /* d */, double scale, double noise_var,
+                              const double* mean_c);
 /* update(model, xs, ys) (StandardGP.jl:79-83, GradientGP.jl:659-668): K + noise*I, Cholesky,
  * alpha.  *info = 0, or the 1-based failing pivot in the caller's out-major ordering is NOT
  * guaranteed — only info > 0 is (status ABO_ERR_NOT_POSDEF); the handle is then un-fitted. */
@@ -160,6 +165,11 @@ int32_t abo_acq_eval_grad(abo_gp* gp, int32_t acq_id, const double* params, cons
  * posterior. */
 int32_t abo_nlml_batch(abo_gp* gp, const double* X, const double* y, int64_t n,
                        const double* logparams, int64_t R, double* nlml, double* grad, int32_t* info);
+
+/* the same for ARD parameter vectors {log l_1 .. log l_d, log sig2}: logparams R x (d+1), grad R x (d+1) (the extension of the
+ * nlml parameter vector the reference plans at bayesian_opt.jl:193-194); StandardGP (p = 1), d <= 32. */
+int32_t abo_nlml_batch_ard(abo_gp* gp, const double* X, const double* y, int64_t n,
+                           const double* logparams, int64_t R, double* nlml, double* grad, int32_t* info);
 
 /* monte_carlo_fill_distance (src/BO_utils.jl:140-159): max over the m sample points S (m x d) of the
  * distance to the nearest of the n training points X (n x d); the caller draws the samples. */

@@ -7,7 +7,7 @@
 module AboCuda
 
 using LinearAlgebra
-import AbstractGPs, ForwardDiff
+import AbstractGPs, ForwardDiff, KernelFunctions
 using ..AbstractBayesOpt: AbstractSurrogate, AbstractAcquisition, ExpectedImprovement,
     ProbabilityImprovement, UpperConfidenceBound, GradientNormUCB, EnsembleAcquisition, StandardGP, GradientGP,
     extract_scale_and_lengthscale
@@ -47,6 +47,20 @@ end
 const KERNEL_IDS = Dict(:SqExponentialKernel => 0, :Matern52Kernel => 1, :Matern72Kernel => 2,
     :ApproxMatern52Kernel => 3, :ApproxMatern72Kernel => 4, :ADMatern52Kernel => 5, :ADMatern72Kernel => 6)
 
+# hyper-parameters of a handle: ScaleTransform (one stored s = 1/l, SURVEY H4) or ARDTransform (one per dimension — not
+# constructible through the reference's constructors today, src/bayesian_opt.jl:193-194 lists it as a TODO, but a kernel
+# built by hand with `base ∘ ARDTransform(1 ./ l)` is honoured by every device path)
+function set_params!(h, transform, scale::Float64, noise::Float64, mc::Vector{Float64})
+    if transform isa KernelFunctions.ARDTransform
+        v = collect(Float64, transform.v)
+        check(GC.@preserve v mc ccall((:abo_gp_set_params_ard, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, Ptr{Float64}),
+            h.h, v, scale, noise, mc))
+    else
+        check(GC.@preserve mc ccall((:abo_gp_set_params, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, Ptr{Float64}),
+            h.h, Float64(transform.s[1]), scale, noise, mc))
+    end
+end
+
 """GPU twin of StandardGP (src/surrogates/StandardGP.jl:11-16): same prior description, the posterior
 is a device handle instead of an AbstractGPs.PosteriorGP."""
 struct CuStandardGP{T} <: AbstractSurrogate
@@ -69,6 +83,7 @@ std_y(m::CuStandardGP, ys, μ, σ) = std_y(m.prior, ys, μ, σ)
 rescale_model(m::CuStandardGP, σ) = CuStandardGP(rescale_model(m.prior, σ), nothing)
 _update_model_parameters(m::CuStandardGP, k) = CuStandardGP(_update_model_parameters(m.prior, k), nothing)
 
+transform_of(m::CuStandardGP) = m.prior.gp.kernel.kernel.transform
 kernel_id(m::CuStandardGP) = KERNEL_IDS[nameof(typeof(get_kernel_constructor(m)))]
 inv_lengthscale(m::CuStandardGP) = m.prior.gp.kernel.kernel.transform.s[1]   # the stored s, not 1/ℓ (SURVEY H4)
 mean_const(m::CuStandardGP) = m.prior.gp.mean isa AbstractGPs.ZeroMean ? 0.0 : m.prior.gp.mean.c
@@ -103,8 +118,7 @@ function update(m::CuStandardGP, xs::Vector, ys::Vector)                      # 
         ctx().h, kernel_id(m), d, 1, r))
     h = Handle(r[])
     mc = [Float64(mean_const(m))]
-    check(ccall((:abo_gp_set_params, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, Ptr{Float64}),
-        h.h, inv_lengthscale(m), get_scale(m)[1], m.prior.noise_var, mc))
+    set_params!(h, transform_of(m), Float64(get_scale(m)[1]), Float64(m.prior.noise_var), mc)
     info = Ref{Int64}(0)
     rc = GC.@preserve X y ccall((:abo_gp_fit, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ref{Int64}),
         h.h, X, y, n, info)
@@ -162,8 +176,7 @@ function nlml_value_grad(m::CuStandardGP, θ::Vector{Float64}, xs, ys)
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:abo_gp_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}), ctx().h, kernel_id(m), d, 1, r))
     h = Handle(r[]); mc = [Float64(mean_const(m))]
-    check(ccall((:abo_gp_set_params, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, Ptr{Float64}),
-        h.h, inv_lengthscale(m), get_scale(m)[1], m.prior.noise_var, mc))
+    set_params!(h, transform_of(m), Float64(get_scale(m)[1]), Float64(m.prior.noise_var), mc)
     val = Ref{Float64}(0.0); g = zeros(2); info = Ref{Int32}(0)
     check(GC.@preserve X y θ g ccall((:abo_nlml_batch, LIB), Int32,
         (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ref{Float64}, Ptr{Float64}, Ref{Int32}),
@@ -213,6 +226,7 @@ std_y(m::CuGradientGP, ys, μ, σ) = std_y(m.prior, ys, μ, σ)
 rescale_model(m::CuGradientGP, σ) = CuGradientGP(rescale_model(m.prior, σ), nothing)
 _update_model_parameters(m::CuGradientGP, k) = CuGradientGP(_update_model_parameters(m.prior, k), nothing)
 
+transform_of(m::CuGradientGP) = m.prior.gp.kernel.base_kernel.kernel.transform
 kernel_id(m::CuGradientGP) = KERNEL_IDS[nameof(typeof(get_kernel_constructor(m)))]
 inv_lengthscale(m::CuGradientGP) = m.prior.gp.kernel.base_kernel.kernel.transform.s[1]   # stored s (GradientGP.jl:842)
 # gradConstMean's constructor returns a CustomMean closing over c (GradientGP.jl:505-515): evaluate it per output
@@ -245,8 +259,7 @@ function update(m::CuGradientGP, xs::AbstractVector, ys::AbstractVector)   # Gra
         ctx().h, kernel_id(m), d, p, r))
     h = Handle(r[])
     mc = mean_consts(m, X[:, 1])
-    check(ccall((:abo_gp_set_params, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, Ptr{Float64}),
-        h.h, inv_lengthscale(m), get_scale(m)[1], m.prior.noise_var, mc))
+    set_params!(h, transform_of(m), Float64(get_scale(m)[1]), Float64(m.prior.noise_var), mc)
     info = Ref{Int64}(0)
     rc = GC.@preserve X y ccall((:abo_gp_fit, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ref{Int64}),
         h.h, X, y, n, info)
@@ -332,8 +345,7 @@ function nlml_value_grad(m::CuGradientGP, θ::Vector{Float64}, xs, ys)
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:abo_gp_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}), ctx().h, kernel_id(m), d, p, r))
     h = Handle(r[]); mc = mean_consts(m, X[:, 1])
-    check(ccall((:abo_gp_set_params, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, Ptr{Float64}),
-        h.h, inv_lengthscale(m), get_scale(m)[1], m.prior.noise_var, mc))
+    set_params!(h, transform_of(m), Float64(get_scale(m)[1]), Float64(m.prior.noise_var), mc)
     val = Ref{Float64}(0.0); g = zeros(2); info = Ref{Int32}(0)
     check(GC.@preserve X y θ g ccall((:abo_nlml_batch, LIB), Int32,
         (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ref{Float64}, Ptr{Float64}, Ref{Int32}),
@@ -360,6 +372,23 @@ function standardize_device(m::Union{CuStandardGP,CuGradientGP}, ys::AbstractVec
         (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
         ctx().h, y, n, p, STD_CHOICE[choice], μ, σ, ystd, best))
     grad ? (μ, σ, [collect(r) for r in eachrow(reshape(ystd, n, p))], best[]) : (μ[1], σ[1], ystd, best[])
+end
+
+# ARD marginal likelihood: θ = (log l_1 .. log l_d, log σ²), value and analytic gradient (d + 1) in one call — the extension
+# of the nlml parameter vector planned at src/bayesian_opt.jl:193-194
+function nlml_ard_value_grad(m::CuStandardGP, θ::Vector{Float64}, xs, ys)
+    X = Matrix{Float64}(points(xs)); d, n = size(X); y = collect(Float64, ys)
+    length(θ) == d + 1 || throw(DimensionMismatch("θ must hold d + 1 entries"))
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:abo_gp_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}), ctx().h, kernel_id(m), d, 1, r))
+    h = Handle(r[]); mc = [Float64(mean_const(m))]
+    set_params!(h, transform_of(m), Float64(get_scale(m)[1]), Float64(m.prior.noise_var), mc)
+    val = Ref{Float64}(0.0); g = zeros(d + 1); info = Ref{Int32}(0)
+    check(GC.@preserve X y θ g ccall((:abo_nlml_batch_ard, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ref{Float64}, Ptr{Float64}, Ref{Int32}),
+        h.h, X, y, n, θ, 1, val, g, info))
+    info[] != 0 && throw(LinearAlgebra.PosDefException(info[]))
+    val[], g
 end
 
 # monte_carlo_fill_distance (src/BO_utils.jl:140-159) on the device; the caller draws the uniform samples

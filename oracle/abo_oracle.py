@@ -101,8 +101,9 @@ def sqdist(Xs: np.ndarray, Ys: np.ndarray, dtype=np.float64) -> np.ndarray:
 def kernelmatrix(kind: int, inv_ls: float, scale: float, X: np.ndarray, Y: np.ndarray | None = None, dtype=np.float64):
     """sigma^2 * kappa(metric(s x, s y))  — ScaledKernel(TransformedKernel(base, ScaleTransform(s)))
     as assembled at src/surrogates/StandardGP.jl:41-64 (s = 1/l is what is stored)."""
-    Xs = np.asarray(X, dtype=dtype) * dtype(inv_ls)
-    Ys = Xs if Y is None else np.asarray(Y, dtype=dtype) * dtype(inv_ls)
+    sv = np.asarray(inv_ls, dtype=dtype)               # scalar (ScaleTransform) or one per dimension (ARDTransform)
+    Xs = np.asarray(X, dtype=dtype) * sv
+    Ys = Xs if Y is None else np.asarray(Y, dtype=dtype) * sv
     p, _, _ = phi_all(kind, sqdist(Xs, Ys, dtype), dtype)
     return dtype(scale) * p
 
@@ -122,9 +123,9 @@ def grad_kernelmatrix(kind, inv_ls, scale, X, Y=None, out_x=None, out_y=None, dt
     m = Y.shape[0]
     out_x = list(range(d + 1)) if out_x is None else list(out_x)
     out_y = list(range(d + 1)) if out_y is None else list(out_y)
-    s = dtype(inv_ls)
+    sv = np.broadcast_to(np.asarray(inv_ls, dtype=dtype), (d,))      # s_k = 1/l_k (all equal for an isotropic kernel)
     scale = dtype(scale)
-    Xs, Ys = X * s, Y * s
+    Xs, Ys = X * sv, Y * sv
     u = sqdist(Xs, Ys, dtype)
     p, dp, ddp = phi_all(kind, u, dtype)
     K = np.empty((len(out_x) * n, len(out_y) * m), dtype=dtype)
@@ -135,11 +136,11 @@ def grad_kernelmatrix(kind, inv_ls, scale, X, Y=None, out_x=None, out_y=None, dt
             if a == 0 and b == 0:
                 blk = scale * p
             elif a > 0 and b == 0:
-                blk = 2 * s * scale * dp * Da
+                blk = 2 * sv[a - 1] * scale * dp * Da
             elif a == 0 and b > 0:
-                blk = -2 * s * scale * dp * Db
+                blk = -2 * sv[b - 1] * scale * dp * Db
             else:
-                blk = -scale * (4 * s * s * ddp * Da * Db + (2 * s * s * dp if a == b else 0.0))
+                blk = -scale * (4 * sv[a - 1] * sv[b - 1] * ddp * Da * Db + (2 * sv[a - 1] ** 2 * dp if a == b else 0.0))
             K[ia * n:(ia + 1) * n, ib * m:(ib + 1) * m] = blk
     return K
 
@@ -237,8 +238,9 @@ def _prior_var(post: Posterior, m, outputs):
     gradient rows -2 s^2 sig2 phi'(0) (the a == b, D = 0 case of grad_kernelmatrix)."""
     p0, dp0, _ = phi_all(post.kind, np.zeros(1))
     v = []
+    sv = np.broadcast_to(np.asarray(post.inv_ls, dtype=np.float64), (post.X.shape[1],))
     for o in outputs:
-        v.append(np.full(m, post.scale * p0[0] if o == 0 else -2 * post.inv_ls ** 2 * post.scale * dp0[0]))
+        v.append(np.full(m, post.scale * p0[0] if o == 0 else -2 * sv[o - 1] ** 2 * post.scale * dp0[0]))
     return np.concatenate(v)
 
 
@@ -321,6 +323,29 @@ def nlml(X, y_flat, kind, log_ls, log_scale, noise, mean_c=None, gradient_gp=Fal
     g_ls = 0.5 * np.sum(M * dK_ls)
     g_sc = 0.5 * np.sum(M * K)
     return val, np.array([g_ls, g_sc])
+
+
+def nlml_ard(X, y, kind, log_ls, log_scale, noise, mean_c=0.0, want_grad=False):
+    """NLML of a StandardGP with one length scale per dimension (ARDTransform; the extension of the nlml parameter vector
+    planned at src/bayesian_opt.jl:193-194) and its analytic gradient with respect to (log l_1 .. log l_d, log sig2):
+    dK/dlog l_k = -2 sig2 phi'(u) D_k^2 with D_k = (x_k - y_k) / l_k,  dK/dlog sig2 = K."""
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+    n, d = X.shape
+    sv = np.exp(-np.asarray(log_ls, dtype=np.float64)); sc = math.exp(log_scale)
+    K = kernelmatrix(kind, sv, sc, X)
+    C = K.copy(); C[np.diag_indices_from(C)] += noise
+    U = _chol_upper(C)
+    delta = np.asarray(y, dtype=np.float64).ravel() - mean_c
+    w = sla.solve_triangular(U, delta, trans="T", lower=False, check_finite=False)
+    val = 0.5 * (n * math.log(2 * math.pi) + 2.0 * np.sum(np.log(np.diag(U))) + float(w @ w))
+    if not want_grad:
+        return val
+    alpha = sla.solve_triangular(U, w, lower=False, check_finite=False)
+    M = sla.cho_solve((U, False), np.eye(n), check_finite=False) - np.outer(alpha, alpha)
+    Xs = X * sv
+    _, dp, _ = phi_all(kind, sqdist(Xs, Xs))
+    g = [0.5 * np.sum(M * (-2.0 * sc * dp * (Xs[:, k][:, None] - Xs[:, k][None, :]) ** 2)) for k in range(d)]
+    return val, np.array(g + [0.5 * np.sum(M * K)])
 
 
 def dK_dlogls(kind, s, sc, X, gradient_gp=False, eps=None):

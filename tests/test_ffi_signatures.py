@@ -16,7 +16,8 @@ def test_julia_ccalls_match_header():
     bound = {c[0] for c in chk.julia_ccalls()}
     # the GradientGP surface and the fused acquisitions are bound, not only the StandardGP path
     for name in ("abo_gp_create", "abo_gp_fit", "abo_gp_append", "abo_gp_clone", "abo_gp_posterior", "abo_gp_posterior_cov",
-                 "abo_acq_eval", "abo_acq_eval_grad", "abo_acq_eval_multi", "abo_nlml_batch", "abo_fill_distance"):
+                 "abo_acq_eval", "abo_acq_eval_grad", "abo_acq_eval_multi", "abo_nlml_batch", "abo_fill_distance",
+                 "abo_gp_set_params", "abo_gp_set_params_ard", "abo_nlml_batch_ard", "abo_standardize"):
         assert name in bound, name
 
 
