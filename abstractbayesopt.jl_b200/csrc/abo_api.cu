@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "sweep_tma.cuh"
 #include "sweep_fused.cuh"
+#include "gemm_tma.cuh"
 #include "abo_internal.h"
 
 using namespace abo;
@@ -58,6 +59,7 @@ static int configure_kernels() {
     CU(cudaFuncSetAttribute(gemm_ws_kernel<KC, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
     CU(cudaFuncSetAttribute(gemm_ws_kernel<MC, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
     CU(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES));
 #define ABO_FS_CFG(DT) CU(cudaFuncSetAttribute(sweep_fused_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem_bytes<DT>()))
     ABO_FS_CFG(4); ABO_FS_CFG(8); ABO_FS_CFG(12); ABO_FS_CFG(16); ABO_FS_CFG(20); ABO_FS_CFG(24); ABO_FS_CFG(32);
 #undef ABO_FS_CFG
@@ -277,10 +279,22 @@ int pinned_get(abo_ctx* c, size_t bytes, void** out) {
 // A: batch matrices, row-major, Npad x Npad (ld), lower triangle referenced.
 // Dinv: batch x T x 128 x 128 block inverses.  info: batch ints (0 = ok).
 // ------------------------------------------------------------------------------------------
+int make_tmap_k4(CUtensorMap* map, const double* base, int64_t K, int64_t rows, int64_t ld);
+static int launch_gemm_tma(abo_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB, TmaGemmParams p, cudaStream_t st);
 int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strideA, double* Dinv, int64_t strideD,
                   int* info, int batch) {
     const int T = (int)(Npad / NB);
     cudaStream_t st = c->stream;
+    // batched, contiguously stacked matrices (the NLML restarts): panel TRSM and trailing SYRK on the persistent TMA pipeline
+    // (both operands k-contiguous; K = 128 per step, so the missing pipeline fill / drain per tile is most of the gain)
+    static const bool tma_env = getenv("ABO_POTRF_TMA") ? atoi(getenv("ABO_POTRF_TMA")) != 0 : true;
+    const bool tma = tma_env && batch > 1 && strideA == Npad * ld && strideD == (int64_t)T * NB * NB;
+    CUtensorMap tmA, tmD;
+    if (tma) {
+        int rc;
+        if ((rc = make_tmap_k4(&tmA, A, Npad, (int64_t)batch * Npad, ld)) || (rc = make_tmap_k4(&tmD, Dinv, NB, (int64_t)batch * T * NB, NB)))
+            return rc;
+    }
     for (int jb = 0; jb < T; ++jb) {
         double* Ajj = A + (int64_t)jb * NB * (ld + 1);
         double* Dj = Dinv + (int64_t)jb * NB * NB;
@@ -289,6 +303,22 @@ int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strid
         const int rem = (int)(Npad - (int64_t)(jb + 1) * NB);
         if (rem <= 0) break;
         double* P = Ajj + (int64_t)NB * ld;            // panel below the diagonal block
+        if (tma) {
+            int rc;
+            TmaGemmParams g{};                         // L_ij = A_ij * inv(L_jj)^T, in place (a tile is read completely before it is written)
+            g.Mt = rem / NB; g.Nt = 1; g.batch = batch; g.K = NB; g.flags = 0; g.alpha = 1.0; g.beta = 0.0;
+            g.a_row0 = (jb + 1) * NB; g.a_rstep = (int)Npad; g.a_col0 = jb * NB; g.a_cstep = 0;
+            g.b_row0 = jb * NB; g.b_rstep = T * NB; g.b_col0 = 0; g.b_cstep = 0;
+            g.C = A; g.ldc = ld; g.c_off0 = (int64_t)(jb + 1) * NB * ld + (int64_t)jb * NB; g.c_zstep = strideA;
+            if ((rc = launch_gemm_tma(c, tmA, tmD, g, st))) return rc;
+            TmaGemmParams q{};                         // A_22 -= L_21 L_21^T (lower tiles)
+            q.Mt = rem / NB; q.Nt = rem / NB; q.batch = batch; q.K = NB; q.flags = LOWER_ONLY; q.alpha = -1.0; q.beta = 1.0;
+            q.a_row0 = (jb + 1) * NB; q.a_rstep = (int)Npad; q.a_col0 = jb * NB; q.a_cstep = 0;
+            q.b_row0 = q.a_row0; q.b_rstep = q.a_rstep; q.b_col0 = q.a_col0; q.b_cstep = 0;
+            q.C = A; q.ldc = ld; q.c_off0 = (int64_t)(jb + 1) * NB * (ld + 1); q.c_zstep = strideA;
+            if ((rc = launch_gemm_tma(c, tmA, tmA, q, st))) return rc;
+            continue;
+        }
         GemmParams g{};
         g.A = P; g.lda = ld; g.strideA = strideA;
         g.B = Dj; g.ldb = NB; g.strideB = strideD;
@@ -567,6 +597,87 @@ int trtri_blocked(abo_ctx* c, const double* L, double* Linv, double* W, int64_t 
     return ABO_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// The same recursion on the TMA pipeline (gemm_tma.cuh): every operand k-contiguous.  Besides X = L^-1 the
+// recursion carries U = X^T (written by the transposed-store epilogue) and keeps the intermediate W21 only as
+// its transpose:     Wt = (L21 U11^T ... ) i.e.  W21^T  <- A = L21, B = U11 (rows of X11^T)
+//                    X21 = -X22 W21               <- A = X22, B = W21^T ;  U12 = X21^T by the same launch
+// Single matrix: all pairs of a level are one launch batched over the pairs; batched matrices (NLML): one
+// launch per pair batched over the matrices.  Wt, U: scratch / output of the shape of L.
+// ------------------------------------------------------------------------------------------
+__global__ void place_diag_both_kernel(const double* __restrict__ Dinv, double* __restrict__ Linv, double* __restrict__ U, int64_t ld,
+                                       int64_t strideD, int64_t strideL) {
+    const int t = blockIdx.x;
+    const double* src = Dinv + (int64_t)blockIdx.y * strideD + (int64_t)t * NB * NB;
+    double* dst = Linv + (int64_t)blockIdx.y * strideL + (int64_t)t * NB * (ld + 1);
+    double* dsu = U + (int64_t)blockIdx.y * strideL + (int64_t)t * NB * (ld + 1);
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+        const int r = e >> 7, cc = e & 127;
+        dst[(int64_t)r * ld + cc] = src[e];
+        dsu[(int64_t)r * ld + cc] = src[cc * NB + r];
+    }
+}
+static int launch_gemm_tma(abo_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB, TmaGemmParams p, cudaStream_t st) {
+    if (p.Mt <= 0 || p.Nt <= 0 || p.batch <= 0) return ABO_OK;
+    const int64_t per = (p.flags & LOWER_ONLY) ? (int64_t)p.Mt * (p.Mt + 1) / 2 : (int64_t)p.Mt * p.Nt;
+    const int64_t total = per * p.batch;
+    if (total > 0x7fffffff) return abo_fail(ABO_ERR_INVALID, "too many tiles in one launch");
+    p.total = (int)total;
+    gemm_tma_kernel<<<(int)std::min<int64_t>(total, c->sms), SW_THREADS, TG_SMEM_BYTES, st>>>(tmA, tmB, p);
+    KL(c);
+    return ABO_OK;
+}
+int trtri_tma(abo_ctx* c, const double* L, double* Linv, double* U, double* Wt, int64_t Npad, int64_t ld, int64_t strideM,
+              const double* Dinv, int64_t strideD, int batch) {
+    const int T = (int)(Npad / NB);
+    cudaStream_t st = c->stream;
+    const int64_t rows = (batch == 1) ? Npad : (int64_t)batch * Npad;        // batched matrices are stacked (strideM = Npad * ld)
+    if (batch > 1 && strideM != Npad * ld) return abo_fail(ABO_ERR_INVALID, "trtri_tma: batched matrices must be contiguous");
+    CUtensorMap tmL, tmX, tmU, tmW;
+    int rc;
+    if ((rc = make_tmap_k4(&tmL, L, Npad, rows, ld)) || (rc = make_tmap_k4(&tmX, Linv, Npad, rows, ld)) ||
+        (rc = make_tmap_k4(&tmU, U, Npad, rows, ld)) || (rc = make_tmap_k4(&tmW, Wt, Npad, rows, ld)))
+        return rc;
+    place_diag_both_kernel<<<dim3(T, batch), 256, 0, st>>>(Dinv, Linv, U, ld, strideD, strideM);
+    KL(c);
+    for (int b = 1; b < T; b <<= 1) {
+        const int npairs = (T - b + 2 * b - 1) / (2 * b), nfull = T / (2 * b);
+        // groups of pairs with equal shapes: (first pair, count, rows of block 22)
+        struct Grp { int q0, nq, rr; };
+        std::vector<Grp> groups;
+        if (nfull > 0) groups.push_back({0, nfull, b});
+        if (npairs > nfull) groups.push_back({nfull, 1, T - 2 * b * nfull - b});
+        for (const Grp& gq : groups) {
+            const int launches = (batch == 1) ? 1 : gq.nq;                  // batched matrices: one launch per pair
+            for (int li = 0; li < launches; ++li) {
+                const int q = gq.q0 + li;
+                const int o = 2 * b * q;
+                const int zb = (batch == 1) ? gq.nq : batch;
+                const int rstep = (batch == 1) ? 2 * b * NB : (int)Npad, cstep = (batch == 1) ? 2 * b * NB : 0;
+                const int64_t zoff = (batch == 1) ? (int64_t)2 * b * NB * (ld + 1) : strideM;
+                TmaGemmParams g{};
+                g.batch = zb; g.alpha = 1.0; g.beta = 0.0;
+                // Wt(o, o+b) = (L21 X11)^T : A = L21, B = U11 (k >= n)
+                g.Mt = gq.rr; g.Nt = b; g.K = b * NB; g.flags = KLO_N;
+                g.a_row0 = (o + b) * NB; g.a_col0 = o * NB; g.a_rstep = rstep; g.a_cstep = cstep;
+                g.b_row0 = o * NB; g.b_col0 = o * NB; g.b_rstep = rstep; g.b_cstep = cstep;
+                g.C = nullptr; g.CT = Wt; g.ldct = ld; g.ct_off0 = (int64_t)o * NB * ld + (int64_t)(o + b) * NB; g.ct_zstep = zoff;
+                if ((rc = launch_gemm_tma(c, tmL, tmU, g, st))) return rc;
+                // X21 = -X22 W21 (k <= m): A = X22, B = W21^T ; U12 = X21^T
+                TmaGemmParams h{};
+                h.batch = zb; h.alpha = -1.0; h.beta = 0.0;
+                h.Mt = gq.rr; h.Nt = b; h.K = gq.rr * NB; h.flags = KHI_M;
+                h.a_row0 = (o + b) * NB; h.a_col0 = (o + b) * NB; h.a_rstep = rstep; h.a_cstep = cstep;
+                h.b_row0 = o * NB; h.b_col0 = (o + b) * NB; h.b_rstep = rstep; h.b_cstep = cstep;
+                h.C = Linv; h.ldc = ld; h.c_off0 = (int64_t)(o + b) * NB * ld + (int64_t)o * NB; h.c_zstep = zoff;
+                h.CT = U; h.ldct = ld; h.ct_off0 = (int64_t)o * NB * ld + (int64_t)(o + b) * NB; h.ct_zstep = zoff;
+                if ((rc = launch_gemm_tma(c, tmX, tmW, h, st))) return rc;
+            }
+        }
+    }
+    return ABO_OK;
+}
+
 // beta = Linv * delta ; alpha = Linv^T * beta      (alpha = (K + noise I)^-1 (y - m))
 int solve_alpha(abo_ctx* c, const double* Linv, int64_t ld, int64_t N, const double* delta, double* beta,
                 double* alpha, int64_t strideM, int64_t strideV, int batch) {
@@ -811,7 +922,12 @@ extern "C" int32_t abo_gp_fit(abo_gp* g, const double* X, const double* y, int64
     if (info_out) *info_out = hinfo;
     if (hinfo != 0)
         return abo_fail(ABO_ERR_NOT_POSDEF, "matrix is not positive definite; Cholesky factorization failed at pivot %d", hinfo);
-    if ((rc = trtri_blocked(c, g->dL, g->dLinv, W, Npad, g->ld, 0, Dinv, 0, 1))) return rc;
+    static const bool tma_inv = getenv("ABO_TRTRI_TMA") ? atoi(getenv("ABO_TRTRI_TMA")) != 0 : true;
+    if (tma_inv && T > 1) {
+        double* U;
+        if ((rc = ws_get(c, WS_TRTRI_U, sizeof(double) * (size_t)Npad * Npad, (void**)&U))) return rc;
+        if ((rc = trtri_tma(c, g->dL, g->dLinv, U, W, Npad, g->ld, 0, Dinv, 0, 1))) return rc;
+    } else if ((rc = trtri_blocked(c, g->dL, g->dLinv, W, Npad, g->ld, 0, Dinv, 0, 1))) return rc;
     if ((rc = solve_alpha(c, g->dLinv, g->ld, Npad, g->dDelta, g->dBeta, g->dAlpha, 0, 0, 1))) return rc;
     CU(cudaStreamSynchronize(st));
     g->fitted = true;

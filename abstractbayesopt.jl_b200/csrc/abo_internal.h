@@ -31,7 +31,7 @@ int abo_fail(int code, const char* fmt, ...);
 enum WsSlot {
     WS_STAGE_X = 0, WS_STAGE_Y, WS_DINV, WS_INFO, WS_TRTRI, WS_VEC_PART, WS_KS, WS_PMEAN, WS_SUMSQ, WS_CAND,
     WS_OUT_A, WS_OUT_B, WS_NLML_K, WS_NLML_LINV, WS_NLML_W, WS_NLML_X, WS_NLML_VEC, WS_NLML_PAR, WS_APPEND,
-    WS_TOPK, WS_SELECT, WS_GRAD_W, WS_GRAD_Z, WS_GRAD_PART, WS_GRAD_OUT, WS_COUNT
+    WS_TOPK, WS_SELECT, WS_GRAD_W, WS_GRAD_Z, WS_GRAD_PART, WS_GRAD_OUT, WS_TRTRI_U, WS_NLML_U, WS_COUNT
 };
 
 struct WsBuf { void* ptr = nullptr; size_t bytes = 0; };
@@ -99,6 +99,8 @@ int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strid
                   int* info, int batch);
 int trtri_blocked(abo_ctx* c, const double* L, double* Linv, double* W, int64_t Npad, int64_t ld, int64_t strideM,
                   const double* Dinv, int64_t strideD, int batch);
+int trtri_tma(abo_ctx* c, const double* L, double* Linv, double* U, double* Wt, int64_t Npad, int64_t ld, int64_t strideM,
+              const double* Dinv, int64_t strideD, int batch);
 int solve_alpha(abo_ctx* c, const double* Linv, int64_t ld, int64_t N, const double* delta, double* beta,
                 double* alpha, int64_t strideM, int64_t strideV, int batch);
 void abo_nccl_teardown(abo_ctx* c);
