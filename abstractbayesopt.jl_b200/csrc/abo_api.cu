@@ -72,6 +72,8 @@ static int ctx_init_resources(abo_ctx* c) {
     CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));    // main / panel stream
     CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));   // look-ahead trailing updates
     CU(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_hi));   // bulk half of the panel chain / copy stream
+    CU(cudaStreamCreateWithPriority(&c->stream4, cudaStreamNonBlocking, prio_lo));   // early part of the triangular inverse
+    CU(cudaEventCreateWithFlags(&c->ev_inv, cudaEventDisableTiming));
     for (int q = 0; q < 3; ++q) CU(cudaEventCreateWithFlags(&c->ev_p[q], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
@@ -109,7 +111,7 @@ extern "C" int32_t abo_ctx_create(int32_t device, abo_ctx** out) {
 static void gp_free_device(abo_gp* g);
 // every stream of the context: workspace slots and caller buffers may be in use on any of them
 void ctx_sync_all(abo_ctx* c) {
-    for (cudaStream_t s_ : {c->stream, c->stream2, c->stream3}) if (s_) cudaStreamSynchronize(s_);
+    for (cudaStream_t s_ : {c->stream, c->stream2, c->stream3, c->stream4}) if (s_) cudaStreamSynchronize(s_);
 }
 
 extern "C" int32_t abo_ctx_destroy(abo_ctx* c) {
@@ -127,7 +129,8 @@ extern "C" int32_t abo_ctx_destroy(abo_ctx* c) {
     auto ev_free = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
     ev_free(c->ev_a); ev_free(c->ev_b);
     for (int q = 0; q < 2; ++q) { ev_free(c->ev_h2d[q]); ev_free(c->ev_pc[q]); }
-    for (cudaStream_t s_ : {c->stream, c->stream2, c->stream3}) if (s_) cudaStreamDestroy(s_);
+    for (cudaStream_t s_ : {c->stream, c->stream2, c->stream3, c->stream4}) if (s_) cudaStreamDestroy(s_);
+    ev_free(c->ev_inv);
     for (int q = 0; q < 3; ++q) ev_free(c->ev_p[q]);
     cudaGetLastError();
     delete c;
@@ -280,7 +283,7 @@ int pinned_get(abo_ctx* c, size_t bytes, void** out) {
 // Dinv: batch x T x 128 x 128 block inverses.  info: batch ints (0 = ok).
 // ------------------------------------------------------------------------------------------
 int make_tmap_k4(CUtensorMap* map, const double* base, int64_t K, int64_t rows, int64_t ld);
-static int launch_gemm_tma(abo_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB, TmaGemmParams p, cudaStream_t st);
+static int launch_gemm_tma(abo_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB, TmaGemmParams p, cudaStream_t st, int max_ctas = 0);
 int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strideA, double* Dinv, int64_t strideD,
                   int* info, int batch) {
     const int T = (int)(Npad / NB);
@@ -360,7 +363,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 //       U_next : the next outer block's columns  -> panel stream (high priority)
 //       U_rest : everything further right        -> second stream, overlaps the next panel
 // ------------------------------------------------------------------------------------------
-int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Dinv, int* info) {
+int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Dinv, int* info, int notify_tile, cudaStream_t notify_stream) {
     const int T = (int)(Npad / NB);
     static const int OB_env = getenv("ABO_POTRF_OB") ? atoi(getenv("ABO_POTRF_OB")) : 3;
     static const bool one_stream = getenv("ABO_POTRF_1STREAM") != nullptr;
@@ -371,7 +374,11 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
     // panel GEMMs: 64-row tiles while the panel is tall (throughput), 32-row tiles once it is short (latency)
     static const int big_rem = getenv("ABO_POTRF_BIGREM") ? atoi(getenv("ABO_POTRF_BIGREM")) : 4096;
     const int OB = std::max(1, OB_env);
-    if (T <= OB) return potrf_blocked(c, A, Npad, ld, 0, Dinv, 0, info, 1);
+    if (T <= OB) {
+        int rc0 = potrf_blocked(c, A, Npad, ld, 0, Dinv, 0, info, 1);
+        if (!rc0 && notify_stream) { CU(cudaEventRecord(c->ev_a, c->stream)); CU(cudaStreamWaitEvent(notify_stream, c->ev_a, 0)); }
+        return rc0;
+    }
     cudaStream_t sp = c->stream, su = one_stream ? c->stream : c->stream2;
     CUtensorMap tmL;
     int rc = make_tmap_k4(&tmL, A, Npad, Npad, ld);
@@ -475,6 +482,13 @@ int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Din
         // ---- U_rest(b) on the second stream: needs panel(b) (event) and, by stream order, U_rest(b-1)
         const int jn = std::min(je + (ramp ? std::min(step + 2, OB) : OB), T);
         CU(cudaEventRecord(c->ev_a, sp));
+        if (notify_stream && notify_tile > 0 && je >= notify_tile) {
+            // every column tile < je of L is final once the panel stream reaches this point (and the bulk rows of the last
+            // TRSM have landed): work that only needs the leading columns may start on `notify_stream` now
+            CU(cudaStreamWaitEvent(notify_stream, c->ev_a, 0));
+            if (boundary_split) CU(cudaStreamWaitEvent(notify_stream, c->ev_p[2], 0));
+            notify_tile = 0;
+        }
         if (jn < T) {
             CU(cudaStreamWaitEvent(su, c->ev_a, 0));
             if (boundary_split) CU(cudaStreamWaitEvent(su, c->ev_p[2], 0));   // the bulk rows of the last TRSM
@@ -617,20 +631,26 @@ __global__ void place_diag_both_kernel(const double* __restrict__ Dinv, double* 
         dsu[(int64_t)r * ld + cc] = src[cc * NB + r];
     }
 }
-static int launch_gemm_tma(abo_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB, TmaGemmParams p, cudaStream_t st) {
+static int launch_gemm_tma(abo_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB, TmaGemmParams p, cudaStream_t st, int max_ctas) {
     if (p.Mt <= 0 || p.Nt <= 0 || p.batch <= 0) return ABO_OK;
     const int64_t per = (p.flags & LOWER_ONLY) ? (int64_t)p.Mt * (p.Mt + 1) / 2 : (int64_t)p.Mt * p.Nt;
     const int64_t total = per * p.batch;
     if (total > 0x7fffffff) return abo_fail(ABO_ERR_INVALID, "too many tiles in one launch");
     p.total = (int)total;
-    gemm_tma_kernel<<<(int)std::min<int64_t>(total, c->sms), SW_THREADS, TG_SMEM_BYTES, st>>>(tmA, tmB, p);
+    gemm_tma_kernel<<<(int)std::min<int64_t>(total, max_ctas > 0 ? max_ctas : c->sms), SW_THREADS, TG_SMEM_BYTES, st>>>(tmA, tmB, p);
     KL(c);
     return ABO_OK;
 }
+// which: 0 everything | 1 only levels b < b_stop plus nothing else | (see trtri_split below).  st / max_ctas: stream and CTA cap.
+static int trtri_tma_on(abo_ctx* c, const double* L, double* Linv, double* U, double* Wt, int64_t Npad, int64_t ld, int64_t strideM,
+                        const double* Dinv, int64_t strideD, int batch, cudaStream_t st, int max_ctas);
 int trtri_tma(abo_ctx* c, const double* L, double* Linv, double* U, double* Wt, int64_t Npad, int64_t ld, int64_t strideM,
               const double* Dinv, int64_t strideD, int batch) {
+    return trtri_tma_on(c, L, Linv, U, Wt, Npad, ld, strideM, Dinv, strideD, batch, c->stream, 0);
+}
+static int trtri_tma_on(abo_ctx* c, const double* L, double* Linv, double* U, double* Wt, int64_t Npad, int64_t ld, int64_t strideM,
+                        const double* Dinv, int64_t strideD, int batch, cudaStream_t st, int max_ctas) {
     const int T = (int)(Npad / NB);
-    cudaStream_t st = c->stream;
     const int64_t rows = (batch == 1) ? Npad : (int64_t)batch * Npad;        // batched matrices are stacked (strideM = Npad * ld)
     if (batch > 1 && strideM != Npad * ld) return abo_fail(ABO_ERR_INVALID, "trtri_tma: batched matrices must be contiguous");
     CUtensorMap tmL, tmX, tmU, tmW;
@@ -662,7 +682,7 @@ int trtri_tma(abo_ctx* c, const double* L, double* Linv, double* U, double* Wt, 
                 g.a_row0 = (o + b) * NB; g.a_col0 = o * NB; g.a_rstep = rstep; g.a_cstep = cstep;
                 g.b_row0 = o * NB; g.b_col0 = o * NB; g.b_rstep = rstep; g.b_cstep = cstep;
                 g.C = nullptr; g.CT = Wt; g.ldct = ld; g.ct_off0 = (int64_t)o * NB * ld + (int64_t)(o + b) * NB; g.ct_zstep = zoff;
-                if ((rc = launch_gemm_tma(c, tmL, tmU, g, st))) return rc;
+                if ((rc = launch_gemm_tma(c, tmL, tmU, g, st, max_ctas))) return rc;
                 // X21 = -X22 W21 (k <= m): A = X22, B = W21^T ; U12 = X21^T
                 TmaGemmParams h{};
                 h.batch = zb; h.alpha = -1.0; h.beta = 0.0;
@@ -671,7 +691,7 @@ int trtri_tma(abo_ctx* c, const double* L, double* Linv, double* U, double* Wt, 
                 h.b_row0 = o * NB; h.b_col0 = (o + b) * NB; h.b_rstep = rstep; h.b_cstep = cstep;
                 h.C = Linv; h.ldc = ld; h.c_off0 = (int64_t)(o + b) * NB * ld + (int64_t)o * NB; h.c_zstep = zoff;
                 h.CT = U; h.ldct = ld; h.ct_off0 = (int64_t)o * NB * ld + (int64_t)(o + b) * NB; h.ct_zstep = zoff;
-                if ((rc = launch_gemm_tma(c, tmX, tmW, h, st))) return rc;
+                if ((rc = launch_gemm_tma(c, tmX, tmW, h, st, max_ctas))) return rc;
             }
         }
     }
@@ -915,17 +935,54 @@ extern "C" int32_t abo_gp_fit(abo_gp* g, const double* X, const double* y, int64
     if ((rc = ws_get(c, WS_INFO, sizeof(int) * 16, (void**)&dinfo))) return rc;
     if ((rc = ws_get(c, WS_TRTRI, sizeof(double) * (size_t)Npad * Npad, (void**)&W))) return rc;
     CU(cudaMemsetAsync(dinfo, 0, sizeof(int) * 16, st));
-    if ((rc = potrf_lookahead(c, g->dL, Npad, g->ld, Dinv, dinfo))) return rc;
+    // Conditioning schedule: the triangular inverse of the LEADING b_top tile columns and the first product of the top level
+    // (W21 = L21 X11) only need the leading columns of L, which are final half-way through the factorisation — they run on a
+    // low-priority stream with a capped grid while the factorisation's chain-bound tail leaves most SMs idle; the trailing
+    // block's inverse and the second product (X21 = -X22 W21) follow once the factorisation is complete.
+    static const bool tma_inv = getenv("ABO_TRTRI_TMA") ? atoi(getenv("ABO_TRTRI_TMA")) != 0 : true;
+    static const int ovl_min = getenv("ABO_FIT_OVERLAP_MIN") ? atoi(getenv("ABO_FIT_OVERLAP_MIN")) : 32;      // tiles; 0 disables
+    static const int ovl_ctas = getenv("ABO_FIT_OVERLAP_CTAS") ? atoi(getenv("ABO_FIT_OVERLAP_CTAS")) : 112;
+    double* U = nullptr;
+    if (tma_inv && T > 1 && (rc = ws_get(c, WS_TRTRI_U, sizeof(double) * (size_t)Npad * Npad, (void**)&U))) return rc;
+    int b_top = 1;
+    while (2 * b_top < T) b_top *= 2;                                  // largest power of two below T: the top-level pair is (0, b_top)
+    const bool overlap = U && ovl_min > 0 && T >= ovl_min;
+    if ((rc = potrf_lookahead(c, g->dL, Npad, g->ld, Dinv, dinfo, overlap ? b_top : 0, overlap ? c->stream4 : nullptr))) return rc;
+    CUtensorMap tmL, tmU;
+    if (overlap) {
+        cudaStream_t s4 = c->stream4;
+        const int64_t nl = (int64_t)b_top * NB;
+        if ((rc = trtri_tma_on(c, g->dL, g->dLinv, U, W, nl, g->ld, 0, Dinv, 0, 1, s4, ovl_ctas))) return rc;
+        if ((rc = make_tmap_k4(&tmL, g->dL, Npad, Npad, g->ld)) || (rc = make_tmap_k4(&tmU, U, Npad, Npad, g->ld))) return rc;
+        TmaGemmParams q{};                                            // Wt(0, b_top) = (L21 X11)^T
+        q.batch = 1; q.alpha = 1.0; q.beta = 0.0; q.Mt = T - b_top; q.Nt = b_top; q.K = b_top * NB; q.flags = KLO_N;
+        q.a_row0 = b_top * NB; q.a_col0 = 0; q.b_row0 = 0; q.b_col0 = 0;
+        q.C = nullptr; q.CT = W; q.ldct = g->ld; q.ct_off0 = (int64_t)b_top * NB;
+        if ((rc = launch_gemm_tma(c, tmL, tmU, q, s4, ovl_ctas))) return rc;
+        CU(cudaEventRecord(c->ev_inv, s4));
+    }
     int hinfo = 0;
     CU(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (info_out) *info_out = hinfo;
-    if (hinfo != 0)
+    if (hinfo != 0) {
+        if (overlap) CU(cudaStreamSynchronize(c->stream4));
         return abo_fail(ABO_ERR_NOT_POSDEF, "matrix is not positive definite; Cholesky factorization failed at pivot %d", hinfo);
-    static const bool tma_inv = getenv("ABO_TRTRI_TMA") ? atoi(getenv("ABO_TRTRI_TMA")) != 0 : true;
-    if (tma_inv && T > 1) {
-        double* U;
-        if ((rc = ws_get(c, WS_TRTRI_U, sizeof(double) * (size_t)Npad * Npad, (void**)&U))) return rc;
+    }
+    if (overlap) {
+        const int64_t off = (int64_t)b_top * NB * (g->ld + 1);
+        if ((rc = trtri_tma_on(c, g->dL + off, g->dLinv + off, U + off, W + off, Npad - (int64_t)b_top * NB, g->ld, 0,
+                               Dinv + (int64_t)b_top * NB * NB, 0, 1, st, 0))) return rc;
+        CU(cudaStreamWaitEvent(st, c->ev_inv, 0));
+        CUtensorMap tmX, tmW;
+        if ((rc = make_tmap_k4(&tmX, g->dLinv, Npad, Npad, g->ld)) || (rc = make_tmap_k4(&tmW, W, Npad, Npad, g->ld))) return rc;
+        TmaGemmParams h{};                                            // X21 = -X22 W21 ;  U12 = X21^T
+        h.batch = 1; h.alpha = -1.0; h.beta = 0.0; h.Mt = T - b_top; h.Nt = b_top; h.K = (T - b_top) * NB; h.flags = KHI_M;
+        h.a_row0 = b_top * NB; h.a_col0 = b_top * NB; h.b_row0 = 0; h.b_col0 = b_top * NB;
+        h.C = g->dLinv; h.ldc = g->ld; h.c_off0 = (int64_t)b_top * NB * g->ld;
+        h.CT = U; h.ldct = g->ld; h.ct_off0 = (int64_t)b_top * NB;
+        if ((rc = launch_gemm_tma(c, tmX, tmW, h, st))) return rc;
+    } else if (U) {
         if ((rc = trtri_tma(c, g->dL, g->dLinv, U, W, Npad, g->ld, 0, Dinv, 0, 1))) return rc;
     } else if ((rc = trtri_blocked(c, g->dL, g->dLinv, W, Npad, g->ld, 0, Dinv, 0, 1))) return rc;
     if ((rc = solve_alpha(c, g->dLinv, g->ld, Npad, g->dDelta, g->dBeta, g->dAlpha, 0, 0, 1))) return rc;

@@ -39,7 +39,8 @@ struct WsBuf { void* ptr = nullptr; size_t bytes = 0; };
 struct abo_ctx {
     int device = 0;
     int sms = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;   // 4: triangular inverse of the leading block, overlapping the factorisation's tail
+    cudaEvent_t ev_inv = nullptr;
     cudaEvent_t ev_p[3] = {nullptr, nullptr, nullptr};            // panel-chain split of the Cholesky
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_pc[2] = {nullptr, nullptr};  // candidate pieces: staged / evaluated
@@ -95,6 +96,7 @@ void ctx_sync_all(abo_ctx* c);
 void ws_release(abo_ctx* c, int slot);
 int ws_get(abo_ctx* c, int slot, size_t bytes, void** out);
 int pinned_get(abo_ctx* c, size_t bytes, void** out);
+int potrf_lookahead(abo_ctx* c, double* A, int64_t Npad, int64_t ld, double* Dinv, int* info, int notify_tile = 0, cudaStream_t notify_stream = nullptr);
 int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strideA, double* Dinv, int64_t strideD,
                   int* info, int batch);
 int trtri_blocked(abo_ctx* c, const double* L, double* Linv, double* W, int64_t Npad, int64_t ld, int64_t strideM,
