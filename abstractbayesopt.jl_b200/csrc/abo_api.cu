@@ -1216,6 +1216,17 @@ extern "C" int32_t abo_gp_posterior(abo_gp* g, const double* Xc, int64_t m, int3
     return ABO_OK;
 }
 
+// W = L^-1 K*^T  [Npad][ncol]  (k <= row): both operands k-contiguous -> the persistent TMA GEMM
+static int linv_times_ks(abo_ctx* c, const abo_gp* g, const double* Ks, int64_t ncol, double* W, cudaStream_t st) {
+    CUtensorMap tmX, tmK;
+    int rc;
+    if ((rc = make_tmap_k4(&tmX, g->dLinv, g->Npad, g->Npad, g->ld)) || (rc = make_tmap_k4(&tmK, Ks, g->Npad, ncol, g->Npad))) return rc;
+    TmaGemmParams w{};
+    w.batch = 1; w.alpha = 1.0; w.beta = 0.0; w.Mt = (int)(g->Npad / NB); w.Nt = (int)(ncol / NB); w.K = (int)g->Npad; w.flags = KHI_M;
+    w.C = W; w.ldc = ncol;
+    return launch_gemm_tma(c, tmX, tmK, w, st);
+}
+
 // ------------------------------------------------------------------------------------------
 // acquisition value + analytic gradient for a batch of points
 // ------------------------------------------------------------------------------------------
@@ -1258,11 +1269,7 @@ extern "C" int32_t abo_acq_eval_grad(abo_gp* g, int32_t acq_id, const double* pa
         const int64_t mpad = (mvalid + NB - 1) / NB * NB;
         if ((rc = launch_ks_d(c, g, dXc, c0, m, 0, Ks, pmean, mpad, mc, npb, st))) return rc;
         KL(c);
-        GemmParams w{};                                        // W = L^-1 K*^T   (k <= row)
-        w.A = g->dLinv; w.lda = g->ld; w.B = Ks; w.ldb = Npad; w.C = W; w.ldc = mpad;
-        w.M = (int)Npad; w.N = (int)mpad; w.K = (int)Npad; w.alpha = 1.0; w.beta = 0.0; w.flags = KHI_M;
-        CU((launch_gemm<KC, KC, EPI_STORE>(w, 1, st)));
-        KL(c);
+        if ((rc = linv_times_ks(c, g, Ks, mpad, W, st))) return rc;      // W = L^-1 K*^T   (k <= row)
         colsumsq_kernel<<<(unsigned)((mpad + 127) / 128), 128, 0, st>>>(W, Npad, mpad, colsq);
         KL(c);
         GemmParams z{};                                        // Z = L^-T W      (k >= row)
@@ -1315,11 +1322,7 @@ extern "C" int32_t abo_gp_posterior_cov(abo_gp* g, const double* Xc, int64_t m, 
         double* pm = pmean + (size_t)bo * mp;                      // (unused partial means)
         if ((rc = launch_ks_d(c, g, dXc, 0, m, bo, Kb, pm, mp, Mpad, npb, st))) return rc;
     }
-    GemmParams w{};                                                // W = L^-1 K*^T
-    w.A = g->dLinv; w.lda = g->ld; w.B = Ks; w.ldb = Npad; w.C = W; w.ldc = Mpad;
-    w.M = (int)Npad; w.N = (int)Mpad; w.K = (int)Npad; w.alpha = 1.0; w.beta = 0.0; w.flags = KHI_M;
-    CU((launch_gemm<KC, KC, EPI_STORE>(w, 1, st)));
-    KL(c);
+    if ((rc = linv_times_ks(c, g, Ks, Mpad, W, st))) return rc;          // W = L^-1 K*^T
     GemmParams q{};                                                // G = W^T W
     q.A = W; q.lda = Mpad; q.B = W; q.ldb = Mpad; q.C = G; q.ldc = Mpad;
     q.M = (int)Mpad; q.N = (int)Mpad; q.K = (int)Npad; q.alpha = 1.0; q.beta = 0.0; q.flags = 0;

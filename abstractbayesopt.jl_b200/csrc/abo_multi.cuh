@@ -59,11 +59,7 @@ extern "C" int32_t abo_acq_eval_multi(abo_gp* g, int32_t nmem, const int32_t* ac
         CU(cudaMemsetAsync(Ks + (size_t)mp * p * Npad, 0, sizeof(double) * (size_t)(Mpad - mp * p) * Npad, st));   // padding rows
         for (int bo = 0; bo < p; ++bo)
             if ((rc = launch_ks_d(c, g, dXc, c0, m, bo, Ks + (size_t)bo * mp * Npad, pmean + (size_t)bo * mp, mp, Mpad, npb, st))) return rc;
-        GemmParams w{};                                            // W = L^-1 K*^T  [Npad][Mpad]
-        w.A = g->dLinv; w.lda = g->ld; w.B = Ks; w.ldb = Npad; w.C = W; w.ldc = Mpad;
-        w.M = (int)Npad; w.N = (int)Mpad; w.K = (int)Npad; w.alpha = 1.0; w.beta = 0.0; w.flags = KHI_M;
-        CU((launch_gemm<KC, KC, EPI_STORE>(w, 1, st)));
-        KL(c);
+        if ((rc = linv_times_ks(c, g, Ks, Mpad, W, st))) return rc;      // W = L^-1 K*^T  [Npad][Mpad] on the TMA pipeline
         gram_blocks_partial_kernel<<<dim3((unsigned)(((int64_t)npair * mc + 255) / 256), nchunks), 256, 0, st>>>(W, Mpad, g->N, mp, mc, p, part);
         KL(c);
         acq_multi_finish_kernel<<<(unsigned)((mc + 127) / 128), 128, 0, st>>>(gp_spec(g), ms, g->dMeanC, pmean, npb, Mpad, part, nchunks, mp,
