@@ -263,6 +263,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    local_top = [None]
+
     def step_dev(timed=False):
         """One BO iteration of the hot path; every call of the library is synchronous, so host timers bracket
         device work (the device-side total is taken with CUDA events around the K steps)."""
@@ -278,6 +280,7 @@ def main():
         t.append(time.perf_counter())
         ti, tv = h.acq_eval_dev(acq.acq_id, params, Xc_dev.data_ptr(), m, scores_dev.data_ptr(), k=TOPK)
         t.append(time.perf_counter())
+        local_top[0] = (ti, tv)
         if world > 1:
             ti, tv = ctx.topk_allgather(TOPK, ti + rank * m, tv)      # global indices: rank r owns [r m, (r+1) m)
         t.append(time.perf_counter())
@@ -329,6 +332,8 @@ def main():
     #      the same global top-100 (indices AND values) as the sharded run
     xrank = None
     if world > 1:
+        shard_tops = [None] * world
+        dist.all_gather_object(shard_tops, (np.asarray(local_top[0][0]), np.asarray(local_top[0][1])))
         if rank == 0:
             from abo_b200.parallel import merge_topk
             idxs, vals = [], []
@@ -339,8 +344,17 @@ def main():
                 idxs.append(ti_r + r * m); vals.append(tv_r)
                 del Xr
             gi, gv = merge_topk(idxs, vals, TOPK)
-            xrank = {"global_top100_equals_single_gpu": bool(np.array_equal(gi, top_idx) and np.array_equal(gv, top_val)),
+            same_i = np.array_equal(gi, top_idx); same_v = np.array_equal(gv, top_val)
+            shard_ok = [bool(np.array_equal(shard_tops[r][0] + r * m, idxs[r]) and np.array_equal(shard_tops[r][1], vals[r]))
+                        for r in range(world)]
+            xrank = {"global_top100_equals_single_gpu": bool(same_i and same_v), "per_shard_top100_equal": shard_ok,
                      "argmax_global_index": int(top_idx[0])}
+            if not (same_i and same_v):
+                nb = min(len(gi), len(top_idx))
+                bad = [int(q) for q in np.flatnonzero((gi[:nb] != top_idx[:nb]) | (gv[:nb] != top_val[:nb]))[:5]]
+                xrank["first_mismatches"] = [{"pos": q, "sharded": [int(top_idx[q]), float(top_val[q])], "single": [int(gi[q]), float(gv[q])],
+                                              "owner_rank_sharded": int(top_idx[q] // m), "owner_rank_single": int(gi[q] // m)} for q in bad]
+                xrank["lengths"] = [int(len(top_idx)), int(len(gi))]
         barrier()
 
     # ---- e2e: host buffers through the C-ABI call, copies inside the timed region
