@@ -1,5 +1,5 @@
 """Determinism stress of the sharded BO iteration (bench.py's step) at N ranks:
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/multi_gpu_stress.py [--n 8192] [--cands M] [--iters K]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/multi_gpu_stress.py [--nobs 8192] [--cands M] [--iters K]
 Every iteration repeats clone + append + posterior broadcast + sweep + top-k all-gather on IDENTICAL inputs; each rank
 compares the bit pattern of its whole score vector and of its local / the global top-100 with iteration 0 and reports
 every difference (count, the candidate tiles they fall in, largest deviation).  Exit code 1 on any difference."""
@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import abo_b200 as abo  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=8192)
+ap.add_argument("--nobs", type=int, default=8192)
 ap.add_argument("--d", type=int, default=20)
 ap.add_argument("--cands", type=int, default=1 << 18)
 ap.add_argument("--iters", type=int, default=20)
@@ -25,7 +25,7 @@ if world > 1:
 ctx = abo.Context(lrank)
 if world > 1:
     abo.init_nccl_context(ctx)
-n, d, m = args.n, args.d, args.cands
+n, d, m = args.nobs, args.d, args.cands
 rng = np.random.default_rng(7)
 X = rng.random((n, d)); y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(n)
 kern = 1.0 * abo.with_lengthscale(abo.SqExponentialKernel(), 1.5)
