@@ -494,25 +494,28 @@ def mp_posterior_standard(X, y, kind, inv_ls, scale, noise, mean_c, Xc, dps=50):
     return means, vars_
 
 
-def ld_posterior_truth(post: Posterior, Xc, iters=5):
-    """80-bit arbiter at FULL problem size (SURVEY H3, §8c "arbiter"): posterior mean / variance of the value
-    output at a handful of query points, accurate to ~1e-18 relative to the problem scale.
+def ld_posterior_truth(post: Posterior, Xc, iters=5, outputs=(0,)):
+    """80-bit arbiter at FULL problem size (SURVEY H3, §8c "arbiter"): posterior mean / variance of the outputs
+    `outputs` (0 = value, a = d/dx_a; out-major like posterior_mean_var) at a handful of query points, accurate to
+    ~1e-18 relative to the problem scale.
     The kernel matrix is evaluated in long double from the same FP64 inputs; K z = b is solved by iterative
     refinement: FP64 LAPACK Cholesky as the preconditioner, residuals b - K z accumulated in long double
     (converges geometrically while cond(K) * 2^-53 < 1).  Returns (mean, var) as long double arrays."""
     LD = np.longdouble
     Xc = np.atleast_2d(np.asarray(Xc, dtype=np.float64))
     mc = Xc.shape[0]
+    outputs = list(outputs)
     if post.p == 1:
+        assert outputs == [0]
         K = kernelmatrix(post.kind, post.inv_ls, post.scale, post.X, dtype=LD)
         Ks = kernelmatrix(post.kind, post.inv_ls, post.scale, post.X, Xc, dtype=LD)
     else:
         K = grad_kernelmatrix(post.kind, post.inv_ls, post.scale, post.X, dtype=LD)
-        Ks = grad_kernelmatrix(post.kind, post.inv_ls, post.scale, post.X, Xc, out_y=[0], dtype=LD)
+        Ks = grad_kernelmatrix(post.kind, post.inv_ls, post.scale, post.X, Xc, out_y=outputs, dtype=LD)
     K[np.diag_indices_from(K)] += LD(post.noise)
     B = np.concatenate([post.delta.astype(LD)[:, None], Ks], axis=1)          # delta is exact in FP64 (y - m)
     Z = np.zeros_like(B)
-    scale_b = np.max(np.abs(B), axis=0)
+    scale_b = np.maximum(np.max(np.abs(B), axis=0), LD(1e-300))
     for it in range(iters):
         R = B - K @ Z
         Z = Z + sla.cho_solve((post.U, False), R.astype(np.float64), check_finite=False).astype(LD)
@@ -520,10 +523,10 @@ def ld_posterior_truth(post: Posterior, Xc, iters=5):
             break
     resid = np.max(np.abs(B - K @ Z), axis=0) / scale_b
     alpha = Z[:, 0]
-    mean = LD(post.mean_c[0]) + Ks.T @ alpha
+    mean = np.repeat(np.asarray([post.mean_c[o] for o in outputs], dtype=LD), mc) + Ks.T @ alpha
     q = np.einsum("ij,ij->j", Ks, Z[:, 1:])
-    var = (LD(post.scale) - q) + LD(JITTER)
-    assert mean.shape == (mc,)
+    var = (_prior_var(post, mc, outputs).astype(LD) - q) + LD(JITTER)
+    assert mean.shape == (mc * len(outputs),)
     return mean, var, float(np.max(resid))
 
 
