@@ -298,6 +298,11 @@ int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strid
         if ((rc = make_tmap_k4(&tmA, A, Npad, (int64_t)batch * Npad, ld)) || (rc = make_tmap_k4(&tmD, Dinv, NB, (int64_t)batch * T * NB, NB)))
             return rc;
     }
+    // two-level blocking of the batched path: inside an outer block of OB tile columns the SYRK touches the block's own
+    // columns only (K = 128); everything to the right is updated ONCE per outer block with K = OB * 128, i.e. one
+    // read-modify-write of the trailing tiles per OB panels instead of one per panel
+    static const int ob_env = getenv("ABO_POTRF_BATCH_OB") ? atoi(getenv("ABO_POTRF_BATCH_OB")) : 2;
+    const int OB = tma ? std::max(1, ob_env) : 1;
     for (int jb = 0; jb < T; ++jb) {
         double* Ajj = A + (int64_t)jb * NB * (ld + 1);
         double* Dj = Dinv + (int64_t)jb * NB * NB;
@@ -308,18 +313,30 @@ int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strid
         double* P = Ajj + (int64_t)NB * ld;            // panel below the diagonal block
         if (tma) {
             int rc;
+            const int ob0 = jb / OB * OB, obend = std::min(ob0 + OB, T);      // this panel's outer block [ob0, obend)
             TmaGemmParams g{};                         // L_ij = A_ij * inv(L_jj)^T, in place (a tile is read completely before it is written)
             g.Mt = rem / NB; g.Nt = 1; g.batch = batch; g.K = NB; g.flags = 0; g.alpha = 1.0; g.beta = 0.0;
             g.a_row0 = (jb + 1) * NB; g.a_rstep = (int)Npad; g.a_col0 = jb * NB; g.a_cstep = 0;
             g.b_row0 = jb * NB; g.b_rstep = T * NB; g.b_col0 = 0; g.b_cstep = 0;
             g.C = A; g.ldc = ld; g.c_off0 = (int64_t)(jb + 1) * NB * ld + (int64_t)jb * NB; g.c_zstep = strideA;
             if ((rc = launch_gemm_tma(c, tmA, tmD, g, st))) return rc;
-            TmaGemmParams q{};                         // A_22 -= L_21 L_21^T (lower tiles)
-            q.Mt = rem / NB; q.Nt = rem / NB; q.batch = batch; q.K = NB; q.flags = LOWER_ONLY; q.alpha = -1.0; q.beta = 1.0;
-            q.a_row0 = (jb + 1) * NB; q.a_rstep = (int)Npad; q.a_col0 = jb * NB; q.a_cstep = 0;
-            q.b_row0 = q.a_row0; q.b_rstep = q.a_rstep; q.b_col0 = q.a_col0; q.b_cstep = 0;
-            q.C = A; q.ldc = ld; q.c_off0 = (int64_t)(jb + 1) * NB * (ld + 1); q.c_zstep = strideA;
-            if ((rc = launch_gemm_tma(c, tmA, tmA, q, st))) return rc;
+            const int nin = obend - jb - 1;            // tile columns of the outer block still to the right of this panel
+            if (nin > 0) {
+                TmaGemmParams q{};                     // columns jb+1 .. obend-1: A -= L_panel L_panel^T (lower tiles), K = 128
+                q.Mt = rem / NB; q.Nt = nin; q.batch = batch; q.K = NB; q.flags = LOWER_ONLY; q.alpha = -1.0; q.beta = 1.0;
+                q.a_row0 = (jb + 1) * NB; q.a_rstep = (int)Npad; q.a_col0 = jb * NB; q.a_cstep = 0;
+                q.b_row0 = q.a_row0; q.b_rstep = q.a_rstep; q.b_col0 = q.a_col0; q.b_cstep = 0;
+                q.C = A; q.ldc = ld; q.c_off0 = (int64_t)(jb + 1) * NB * (ld + 1); q.c_zstep = strideA;
+                if ((rc = launch_gemm_tma(c, tmA, tmA, q, st))) return rc;
+            }
+            if (jb == obend - 1 && obend < T) {
+                TmaGemmParams q{};                     // columns >= obend: A -= L_block L_block^T, K = (obend - ob0) * 128
+                q.Mt = T - obend; q.Nt = T - obend; q.batch = batch; q.K = (obend - ob0) * NB; q.flags = LOWER_ONLY; q.alpha = -1.0; q.beta = 1.0;
+                q.a_row0 = obend * NB; q.a_rstep = (int)Npad; q.a_col0 = ob0 * NB; q.a_cstep = 0;
+                q.b_row0 = q.a_row0; q.b_rstep = q.a_rstep; q.b_col0 = q.a_col0; q.b_cstep = 0;
+                q.C = A; q.ldc = ld; q.c_off0 = (int64_t)obend * NB * (ld + 1); q.c_zstep = strideA;
+                if ((rc = launch_gemm_tma(c, tmA, tmA, q, st))) return rc;
+            }
             continue;
         }
         GemmParams g{};
@@ -633,7 +650,8 @@ __global__ void place_diag_both_kernel(const double* __restrict__ Dinv, double* 
 }
 static int launch_gemm_tma(abo_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB, TmaGemmParams p, cudaStream_t st, int max_ctas) {
     if (p.Mt <= 0 || p.Nt <= 0 || p.batch <= 0) return ABO_OK;
-    const int64_t per = (p.flags & LOWER_ONLY) ? (int64_t)p.Mt * (p.Mt + 1) / 2 : (int64_t)p.Mt * p.Nt;
+    if ((p.flags & LOWER_ONLY) && p.Nt > p.Mt) return abo_fail(ABO_ERR_INVALID, "gemm_tma: LOWER_ONLY needs Nt <= Mt");
+    const int64_t per = (p.flags & LOWER_ONLY) ? (int64_t)p.Nt * (p.Nt + 1) / 2 + (int64_t)(p.Mt - p.Nt) * p.Nt : (int64_t)p.Mt * p.Nt;
     const int64_t total = per * p.batch;
     if (total > 0x7fffffff) return abo_fail(ABO_ERR_INVALID, "too many tiles in one launch");
     p.total = (int)total;

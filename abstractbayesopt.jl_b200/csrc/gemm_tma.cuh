@@ -36,11 +36,15 @@ __device__ __forceinline__ TgTile tg_decode(const TmaGemmParams& p, int t) {
     w.z = t % p.batch;
     const int tl = t / p.batch;
     int mt, nt;
-    if (p.flags & LOWER_ONLY) {                     // square tile grid, lower triangle, rows ascending (with KLO_M: heaviest first)
-        mt = (int)((sqrt(8.0 * tl + 1.0) - 1.0) * 0.5);
-        while ((mt + 1) * (mt + 2) / 2 <= tl) ++mt;
-        while (mt * (mt + 1) / 2 > tl) --mt;
-        nt = tl - mt * (mt + 1) / 2;
+    if (p.flags & LOWER_ONLY) {                     // lower tiles nt <= min(mt, Nt - 1) of an Mt x Nt grid (Nt <= Mt): the triangle of
+                                                    // the first Nt tile rows, then full rows of Nt tiles (a trapezoid when Nt < Mt)
+        const int tri = p.Nt * (p.Nt + 1) / 2;
+        if (tl < tri) {
+            mt = (int)((sqrt(8.0 * tl + 1.0) - 1.0) * 0.5);
+            while ((mt + 1) * (mt + 2) / 2 <= tl) ++mt;
+            while (mt * (mt + 1) / 2 > tl) --mt;
+            nt = tl - mt * (mt + 1) / 2;
+        } else { mt = p.Nt + (tl - tri) / p.Nt; nt = (tl - tri) % p.Nt; }
     } else if (p.flags & KLO_N) { nt = tl / p.Mt; mt = tl % p.Mt; }
     else if (p.flags & KHI_M) { mt = p.Mt - 1 - tl / p.Nt; nt = tl % p.Nt; }
     else { mt = tl / p.Nt; nt = tl % p.Nt; }
