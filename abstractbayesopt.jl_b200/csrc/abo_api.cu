@@ -1432,11 +1432,24 @@ static int scores_select_readback(abo_ctx* c, const double* dS, int64_t m, doubl
         if (!hs) { if ((rc = pinned_get(c, sizeof(double) * (size_t)m, (void**)&hs))) return rc; }
         CU(cudaMemcpyAsync(hs, dS, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        std::vector<TopItem> items((size_t)m);
-        for (int64_t i = 0; i < m; ++i) items[(size_t)i] = TopItem{ordkey(hs[i]), i, hs[i]};
+        // heap of the K best seen so far (top = the worst kept); scanning in index order, an element enters only if its key
+        // is strictly larger than the worst kept one, so equal keys keep the smaller index (sortperm is stable)
         auto better = [](const TopItem& a, const TopItem& b) { return a.key != b.key ? a.key > b.key : a.idx < b.idx; };
-        std::partial_sort(items.begin(), items.begin() + K, items.end(), better);
-        for (int64_t i = 0; i < K; ++i) { top_idx[i] = items[(size_t)i].idx; top_val[i] = items[(size_t)i].val; }
+        std::vector<TopItem> keep;
+        keep.reserve((size_t)K);
+        int64_t i = 0;
+        for (; i < K; ++i) keep.push_back(TopItem{ordkey(hs[i]), i, hs[i]});
+        std::make_heap(keep.begin(), keep.end(), better);
+        for (; i < m; ++i) {
+            const uint64_t key = ordkey(hs[i]);
+            if (key > keep.front().key) {
+                std::pop_heap(keep.begin(), keep.end(), better);
+                keep.back() = TopItem{key, i, hs[i]};
+                std::push_heap(keep.begin(), keep.end(), better);
+            }
+        }
+        std::sort(keep.begin(), keep.end(), better);
+        for (int64_t q = 0; q < K; ++q) { top_idx[q] = keep[(size_t)q].idx; top_val[q] = keep[(size_t)q].val; }
         return ABO_OK;
     }
     SelSlot q{};
