@@ -291,7 +291,8 @@ int potrf_blocked(abo_ctx* c, double* A, int64_t Npad, int64_t ld, int64_t strid
     // batched, contiguously stacked matrices (the NLML restarts): panel TRSM and trailing SYRK on the persistent TMA pipeline
     // (both operands k-contiguous; K = 128 per step, so the missing pipeline fill / drain per tile is most of the gain)
     static const bool tma_env = getenv("ABO_POTRF_TMA") ? atoi(getenv("ABO_POTRF_TMA")) != 0 : true;
-    const bool tma = tma_env && batch > 1 && strideA == Npad * ld && strideD == (int64_t)T * NB * NB;
+    // (a single matrix passed with the stacked-layout strides takes the same path: a restart evaluated alone gives the same bits)
+    const bool tma = tma_env && batch >= 1 && strideA == Npad * ld && strideD == (int64_t)T * NB * NB;
     CUtensorMap tmA, tmD;
     if (tma) {
         int rc;
