@@ -17,3 +17,4 @@ class ContinuousDomain(AbstractDomain):
         if not np.all(lower <= upper):
             raise ValueError("lower bounds must be less than or equal to upper bounds")
         self.lower, self.upper = lower, upper
+        self.bounds = [(float(a), float(b)) for a, b in zip(lower, upper)]      # ContinuousDomain.jl: Vector{Tuple}

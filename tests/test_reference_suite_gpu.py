@@ -211,3 +211,30 @@ def test_device_standardisation_matches_reference_formulas(abo, choice):
     g = abo.StandardGP(abo.SqExponentialKernel(), 1e-6)
     mu_h, sd_h = abo.get_mean_std(g, y, choice)
     assert abs(mu_h - mu[0]) <= 1e-14 * max(1.0, abs(mu_h)) and abs(sd_h - sd[0]) <= 1e-14 * sd_h
+
+
+# ---- the reference's own standardisation vectors (test/test_surrogates.jl:107-128, 366-397) on the device kernel and on
+#      the host helpers of the mirror -----------------------------------------------------------------------------------
+def test_reference_standardisation_known_answers(abo):
+    ctx = abo.default_context()
+    y_train = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    mu, sd, ys, best = ctx.standardize(y_train, 5, 1, "mean_scale")
+    assert abs(mu[0] - 3.0) <= 1e-15 and sd[0] > 0                       # "μ ≈ 3.0", "σ > 0"
+    assert abs(np.std(ys, ddof=1) - 1.0) <= 1e-10                        # "std(y_flat_std) ≈ 1.0 atol = 1e-10"
+    g = abo.StandardGP(abo.SqExponentialKernel(), 0.1)
+    mu_h, sd_h = abo.get_mean_std(g, y_train, "mean_scale")
+    assert mu_h == mu[0] and abs(sd_h - sd[0]) <= 1e-15 and np.allclose(abo.std_y(g, y_train, mu_h, sd_h), ys, rtol=0, atol=1e-15)
+    # GradientGP: y_train = [[1, .1, .1], [2, .2, .2], [3, .3, .3]]
+    Y = np.array([[1.0, 0.1, 0.1], [2.0, 0.2, 0.2], [3.0, 0.3, 0.3]])
+    mu_g, sd_g, ys_g, _ = ctx.standardize(Y.T.reshape(-1), 3, 3, "mean_scale")         # out-major, like prep_output
+    assert len(mu_g) == 3 and len(sd_g) == 3
+    assert abs(mu_g[0] - 2.0) <= 1e-15 and mu_g[1] == 0.0 and mu_g[2] == 0.0            # gradients keep a zero mean
+    assert sd_g[0] > 0 and sd_g[1] == sd_g[0] and sd_g[2] == sd_g[0]                    # and the value output's scale
+    Ys = ys_g.reshape(3, 3).T
+    for y_o, y_s in zip(Y, Ys):
+        for a in range(3):
+            assert abs(y_s[a] - (y_o[a] - mu_g[a]) / sd_g[a]) <= 1e-8
+    gg = abo.GradientGP(abo.SqExponentialKernel(), 3, 0.1)
+    mu_hh, sd_hh = abo.get_mean_std(gg, Y, "mean_scale")
+    assert np.allclose(mu_hh, mu_g, rtol=0, atol=1e-15) and np.allclose(sd_hh, sd_g, rtol=1e-15, atol=0)
+    assert np.allclose(abo.std_y(gg, Y, mu_hh, sd_hh), Ys, rtol=0, atol=1e-15)
