@@ -279,6 +279,16 @@ def standardize_problem(BO, choice):
     return BO, (mu, sd)
 
 
+def rescale_output(ys, params):
+    """rescale_output (BO_utils.jl:162-182): standardised observations back on the original scale; (None, None) is the
+    identity."""
+    mu, sd = params
+    if mu is None or sd is None:
+        return [y for y in ys]
+    return [np.asarray(y, dtype=np.float64) * sd + mu if np.ndim(y) else float(y) * float(np.ravel(sd)[0]) + float(np.ravel(mu)[0])
+            for y in ys]
+
+
 def optimize(BO: BOStruct, standardize="mean_scale", hyper_params="all", num_restarts_HP=1, n_grid=10_000,
              n_local=100, rng=None, refine=True, ard=False):
     """optimize(BO; standardize, hyper_params, num_restarts_HP) (bayesian_opt.jl:364-449)."""
