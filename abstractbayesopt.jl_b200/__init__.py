@@ -18,7 +18,7 @@ from .domains import AbstractDomain, ContinuousDomain
 from .parallel import (init_nccl_context, merge_topk, shard_range, sharded_nlml_batch, sharded_restarts, sharded_topk,
                        sync_posterior)
 from .bayesian_opt import (BOStruct, latin_hypercube, lengthscale_bounds, lockstep_lbfgsb, monte_carlo_fill_distance, optimize, optimize_acquisition, optimize_hyperparameters,
-                           rescale_output, standardize_problem, stop_criteria, update_bo)
+                           print_info, rescale_output, standardize_problem, stop_criteria, update_bo)
 
 
 def update(obj, *args, **kw):

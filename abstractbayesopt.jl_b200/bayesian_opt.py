@@ -226,6 +226,25 @@ class BOStruct:
         self.ys_non_std = [np.array(y, dtype=np.float64) for y in y_train]
         self.max_iter, self.iter, self.noise, self.flag = max_iter, 0, noise, False
 
+    def __repr__(self):
+        return _make_info(self)
+
+
+def _make_info(BO):
+    """_make_info / print_info / Base.show(::BOStruct) (BO_utils.jl:5-24)."""
+    return ("== BOStruct Information ==\n"
+            f"Target function: {getattr(BO.func, '__name__', BO.func)}\n"
+            f"Domain: {BO.domain.bounds}\n"
+            f"Number of data points: {len(BO.xs)}\n"
+            f"Acquisition function: {BO.acq}\n"
+            f"Max iterations: {BO.max_iter}\n"
+            f"Noise level: {BO.noise}\n"
+            "=========================")
+
+
+def print_info(BO):
+    print(_make_info(BO))
+
 
 def update_bo(BO: BOStruct, x, y, i):
     """update(BO, x, y, i) (bayesian_opt.jl:113-150): snapshot → push → update → on

@@ -114,3 +114,60 @@ def test_extreme_hyperparameter_values(abo):                                # :9
     small = abo.update(abo.StandardGP(1.0 * abo.with_lengthscale(abo.SqExponentialKernel(), 1e-6), 0.01), x_train, y_train)   # ScaleTransform(1e6)
     pred_small = abo.posterior_mean(small, [0.5])[0]
     assert math.isfinite(pred_large) and math.isfinite(pred_small) and abs(pred_large - pred_small) > 0.01
+
+
+# ---- "BOStruct Tests" (test/test_bayesian_opt.jl:9-223) ---------------------------------------------------------------
+def test_bostruct_construction_update_and_utilities(abo, capsys):
+    f = lambda x: float(np.sum(np.asarray(x) ** 2))
+    domain = abo.ContinuousDomain([-2.0, -2.0], [2.0, 2.0])
+    gp = abo.StandardGP(abo.SqExponentialKernel(), 0.1)
+    x_train = [[-1.0, -1.0], [0.0, 0.0], [1.0, 1.0]]
+    y_train = [f(x) for x in x_train]
+    problem = abo.BOStruct(f, abo.ExpectedImprovement(0.01, min(y_train)), gp, domain, x_train, y_train, 10, 0.1)
+    assert problem.func is f and problem.domain is domain and problem.max_iter == 10 and problem.noise == 0.1      # :10-41
+    assert problem.iter == 0 and problem.flag is False and len(problem.xs) == 3 and len(problem.ys) == 3
+    x_train = [[-1.0, -1.0], [5.0, -5.0]]                                                                          # :43-79
+    y_train = [f(x) for x in x_train]
+    up_gp = abo.update(gp, x_train, y_train)
+    problem = abo.BOStruct(f, abo.ExpectedImprovement(0.01, min(y_train)), up_gp, domain, x_train, y_train, 10, 0.1)
+    x_new = [0.0, 0.0]
+    up = abo.update(problem, x_new, f(x_new), 0)
+    assert len(up.xs) == 3 and len(up.ys) == 3 and list(up.xs[-1]) == x_new and float(up.ys[-1]) == f(x_new)
+    assert up.iter == 1 and up.acq.best_y == 0.0
+    abo.print_info(up)                                                                                             # :81-106
+    out = capsys.readouterr().out
+    assert "== BOStruct Information ==" in out and "Number of data points: 3" in out and "Max iterations: 10" in out
+
+
+def test_hyperparameter_optimisation_returns_a_surrogate(abo):              # :108-137
+    gp = abo.update(abo.StandardGP(abo.SqExponentialKernel(), 0.1), [[-1.0], [0.0], [1.0]], [1.0, 0.0, 1.0])
+    opt = abo.optimize_hyperparameters(gp, [[-1.0], [0.0], [1.0]], [1.0, 0.0, 1.0], [0.0, 0.0], num_restarts=2, scale_std=1.0,
+                                       rng=np.random.default_rng(0))
+    assert isinstance(opt, abo.StandardGP)
+
+
+@pytest.mark.parametrize("mode", ["mean_scale", "scale_only", "mean_only"])
+def test_standardisation_modes(abo, mode):                                  # :139-184
+    f = lambda x: float(np.sum(np.asarray(x) ** 2)) + 10.0
+    domain = abo.ContinuousDomain([-2.0], [2.0])
+    gp = abo.StandardGP(abo.SqExponentialKernel(), 0.1)
+    x_train = [[-1.0], [0.0], [1.0]]
+    y_train = [f(x) for x in x_train]
+    problem = abo.BOStruct(f, abo.ExpectedImprovement(0.01, min(y_train)), gp, domain, x_train, y_train, 10, 0.1)
+    std_problem, params = abo.standardize_problem(problem, mode)
+    mu, sd = params
+    assert float(np.ravel(sd)[0]) > 0 and isinstance(std_problem.model, abo.StandardGP)
+    if mode in ("scale_only", "mean_scale"):
+        assert len(abo.rescale_output(std_problem.ys, params)) == len(problem.ys_non_std)
+
+
+def test_optimisation_loop(abo):                                            # :186-223
+    f = lambda x: (float(np.ravel(x)[0]) - 0.5) ** 2
+    domain = abo.ContinuousDomain([-1.0], [2.0])
+    x_train = [-0.5, 0.0, 1.5]
+    y_train = [f(x) for x in x_train]
+    gp = abo.StandardGP(abo.SqExponentialKernel(), 0.01)
+    problem = abo.BOStruct(f, abo.ExpectedImprovement(0.01, min(y_train)), gp, domain, x_train, y_train, 3, 0.01)
+    result, acq_list, std_params = abo.optimize(problem, standardize=None, hyper_params=None, rng=np.random.default_rng(3))
+    assert len(result.xs) >= len(x_train) and len(result.ys) >= len(y_train) and len(acq_list) >= 0 and result.iter > 0
+    assert min(float(np.ravel(v)[0]) for v in result.ys_non_std) <= min(y_train)
