@@ -1,4 +1,5 @@
-"""Host-side acquisition semantics (constructors, `update`, ensemble weights) with the reference's own test vectors
+"""Host-side mirror of the reference interface (acquisition constructors and `update`, ensemble weights, domains, surrogate
+accessors) with the reference's own test vectors
 (test/test_acquisition.jl:10-18, 45-64, 67-72, 97-114, 117-124, 152-157, 183-201, 204-221, 255-277).  No device needed:
 `update(acq, ys, surrogate)` only looks at the surrogate's TYPE (StandardGP.jl:418, GradientGP.jl:1044)."""
 import numpy as np
@@ -66,3 +67,20 @@ def test_continuous_domain(abo):
     eq = abo.ContinuousDomain([1.0], [1.0])                                 # equal bounds are valid
     assert list(eq.lower) == [1.0] and list(eq.upper) == [1.0]
     assert len(abo.ContinuousDomain([1e6], [1e7]).bounds) == 1
+
+
+def test_surrogate_construction_vectors(abo):
+    """test/test_surrogates.jl:10-57 (StandardGP) and :174-233 (GradientGP): accessors of freshly constructed priors."""
+    for make in (lambda k: abo.StandardGP(k, 0.1), lambda k: abo.GradientGP(k, 3, 0.1)):
+        base = abo.SqExponentialKernel() if make(abo.SqExponentialKernel()).p == 1 else abo.ApproxMatern52Kernel()
+        gp = make(base)
+        assert gp.noise_var == 0.1 and gp.gpx is None
+        assert abo.get_lengthscale(gp)[0] == 1.0 and abo.get_scale(gp)[0] == 1.0
+        gp_custom = make(2.0 * abo.with_lengthscale(base, 0.5))
+        assert abo.get_lengthscale(gp_custom) == [0.5] and abo.get_scale(gp_custom) == [2.0]
+        assert gp_custom.noise_var == 0.1 and gp_custom.gpx is None
+        gp_ls = make(abo.with_lengthscale(base, 0.3))
+        assert abo.get_lengthscale(gp_ls) == [0.3] and abo.get_scale(gp_ls) == [1.0] and gp_ls.gpx is None
+        gp_sc = make(3.0 * base)
+        assert abo.get_lengthscale(gp_sc) == [1.0] and abo.get_scale(gp_sc) == [3.0] and gp_sc.gpx is None
+    assert abo.GradientGP(abo.ApproxMatern52Kernel(), 3, 0.1).p == 3
