@@ -171,3 +171,23 @@ def test_optimisation_loop(abo):                                            # :1
     result, acq_list, std_params = abo.optimize(problem, standardize=None, hyper_params=None, rng=np.random.default_rng(3))
     assert len(result.xs) >= len(x_train) and len(result.ys) >= len(y_train) and len(acq_list) >= 0 and result.iter > 0
     assert min(float(np.ravel(v)[0]) for v in result.ys_non_std) <= min(y_train)
+
+
+# ---- the "Evaluation" testsets of test/test_acquisition.jl (:20-43, :74-95, :126-149, :159-181, :223-253) ----------------
+def test_acquisition_evaluation_vectors(abo):
+    gp = abo.update(abo.StandardGP(abo.SqExponentialKernel(), 0.1), [0.0, 0.5, 1.0], [2.0, 1.0, 0.5])
+    ei, pi, ucb = abo.ExpectedImprovement(0.01, 0.5), abo.ProbabilityImprovement(0.01, 0.5), abo.UpperConfidenceBound(2.0)
+    ei_val = ei(gp, [0.25])[0]
+    assert math.isfinite(ei_val) and ei_val >= 0.0
+    ucb_val = ucb(gp, 0.25)[0]                                               # a bare Real is one 1-D point
+    assert math.isfinite(ucb_val)
+    pi_val = pi(gp, 0.25)[0]
+    assert math.isfinite(pi_val) and 0.0 <= pi_val <= 1.0
+    ens = abo.EnsembleAcquisition([0.6, 0.4], [ei, ucb])
+    ens_val = ens(gp, 0.25)
+    assert np.all(np.isfinite(ens_val))
+    assert np.allclose(ens_val, 0.6 * ei(gp, 0.25) + 0.4 * ucb(gp, 0.25), rtol=1e-12, atol=0)
+    ggp = abo.update(abo.GradientGP(abo.SqExponentialKernel(), 3, 0.1), [[0.0, 0.0], [0.5, 0.5], [1.0, 1.0]],
+                     [[2.0, 0.1, 0.1], [1.0, 0.0, 0.0], [0.5, -0.1, -0.1]])
+    g_val = abo.GradientNormUCB(2.0)(ggp, [[0.25, 0.25]])[0]
+    assert math.isfinite(g_val)
