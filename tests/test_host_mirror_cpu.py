@@ -84,3 +84,19 @@ def test_surrogate_construction_vectors(abo):
         gp_sc = make(3.0 * base)
         assert abo.get_lengthscale(gp_sc) == [1.0] and abo.get_scale(gp_sc) == [3.0] and gp_sc.gpx is None
     assert abo.GradientGP(abo.ApproxMatern52Kernel(), 3, 0.1).p == 3
+
+
+def test_rescale_output_and_print_info(abo, capsys):
+    """rescale_output (BO_utils.jl:162-182) and print_info / show (BO_utils.jl:5-24)."""
+    assert abo.rescale_output([0.5, -1.0], (3.0, 2.0)) == [4.0, 1.0]
+    out = abo.rescale_output([np.array([1.0, 2.0, 3.0])], (np.array([1.0, 0.0, 0.0]), np.array([2.0, 2.0, 2.0])))
+    assert np.array_equal(out[0], [3.0, 4.0, 6.0])
+    assert abo.rescale_output([1.0, 2.0], (None, None)) == [1.0, 2.0]
+    f = lambda x: float(np.sum(np.asarray(x) ** 2))
+    bo = abo.BOStruct(f, abo.ExpectedImprovement(0.01, 0.0), abo.StandardGP(abo.SqExponentialKernel(), 0.1),
+                      abo.ContinuousDomain([-2.0], [2.0]), [-1.0, 0.0, 1.0], [1.0, 0.0, 1.0], 3, 0.1)
+    abo.print_info(bo)
+    text = capsys.readouterr().out
+    for line in ("== BOStruct Information ==", "Number of data points: 3", "Max iterations: 3", "Noise level: 0.1"):
+        assert line in text
+    assert repr(bo).startswith("== BOStruct Information ==")
